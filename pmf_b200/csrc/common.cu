@@ -37,7 +37,7 @@ encode_tiled_fn get_encode_tiled() {
 }
 
 int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box) {
+                  const uint64_t* strides_bytes, const uint32_t* box, bool swizzle32b_atom) {
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) return fail(PMFB_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available (no CUDA driver)");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0)
@@ -59,7 +59,8 @@ int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
                   (unsigned long long)gstr[i]);
   }
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr),
-                   gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle32b_atom ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(PMFB_ERR_CUDA,

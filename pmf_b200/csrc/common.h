@@ -20,8 +20,11 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 encode_tiled_fn get_encode_tiled();
 
 // fp32 tensor map with 128B swizzle and zero OOB fill. strides_bytes has rank-1 entries.
+// swizzle32b_atom=false: SWIZZLE_128B (16B chunks; K-major UMMA operands);
+// swizzle32b_atom=true : SWIZZLE_128B_ATOM_32B (32B chunks; the only layout tcgen05 accepts for
+//                        MN-major tf32 operands, i.e. the wgrad kernel).
 int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box);
+                  const uint64_t* strides_bytes, const uint32_t* box, bool swizzle32b_atom = false);
 
 #define PMFB_CUDA_CHECK(expr)                                                            \
   do {                                                                                   \

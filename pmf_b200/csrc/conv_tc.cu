@@ -254,10 +254,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
           const uint32_t b_addr = a_addr + 4 * kBoxBytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            // MN-major, 128B swizzle: 32 channels contiguous per pixel row, 8 pixel rows per
-            // 1 KB group (one K=8 MMA step); LBO = distance between 32-channel blocks.
-            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 1024, kBoxBytes, 1024);
-            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 1024, kBoxBytes, 1024);
+            // MN-major tf32 operands must use the SWIZZLE_128B_BASE32B layout: 32 channels (128 B)
+            // contiguous per pixel row, 32B chunks XOR-swizzled over 4-row (512 B) atoms.  One K=8
+            // MMA step spans two atoms (SBO = 512 B); LBO = distance between 32-channel blocks.
+            const uint64_t ad = make_smem_desc(a_addr + k * 1024, kBoxBytes, 512, 1u);
+            const uint64_t bd = make_smem_desc(b_addr + k * 1024, kBoxBytes, 512, 1u);
             umma_tf32(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(&ctrl->empty[s]);
@@ -382,9 +383,9 @@ extern "C" int pmfb_conv_wgrad(const pmfb_wgrad_desc* d, void* stream) {
 
   CUtensorMap tmx, tmdy;
   uint32_t box[5] = {32, (uint32_t)d->ptile_w, 1, (uint32_t)d->ptile_h, 1};
-  int rc = make_tmap_f32(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, box);
+  int rc = make_tmap_f32(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, box, true);
   if (rc) return rc;
-  rc = make_tmap_f32(&tmdy, d->dy.ptr, 5, d->dy.dims, d->dy.strides, box);
+  rc = make_tmap_f32(&tmdy, d->dy.ptr, 5, d->dy.dims, d->dy.strides, box, true);
   if (rc) return rc;
 
   WgradK P;
