@@ -1,0 +1,127 @@
+"""The oracle restatements must reproduce the reference's outputs: the committed fixtures everywhere, and
+the live reference whenever /root/reference is present (build container)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import knn_oracle, pmf_oracle as po, project_oracle
+from oracle.ref_loader import reference_available
+from tests import synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+@pytest.mark.parametrize("case", synth.KNN_CASES, ids=lambda c: c["name"])
+def test_knn_oracle_matches_golden(case):
+    inp = synth.knn_inputs(case)
+    out, tie_free = knn_oracle.knn_vote(inp["proj_range"], inp["unproj_range"], inp["proj_argmax"], inp["px"], inp["py"],
+                                        case["knn"], case["search"], case["sigma"], case["cutoff"], case["nclasses"],
+                                        return_aux=True)
+    ref = load("knn_%s.npz" % case["name"])["out"]
+    assert out.shape == ref.shape and out.dtype == np.int64
+    # bit-exact wherever the reference's unordered topk has a unique answer
+    assert np.array_equal(out[tie_free], ref[tie_free])
+    if case["kind"] != "ties":
+        assert tie_free.mean() > 0.99
+        assert (out != ref).mean() < 0.002
+
+
+def test_knn_even_kernel_raises():
+    inp = synth.knn_inputs(synth.KNN_CASES[0])
+    with pytest.raises(ValueError, match="odd"):
+        knn_oracle.knn_vote(inp["proj_range"], inp["unproj_range"], inp["proj_argmax"], inp["px"], inp["py"], 5, 4, 1.0, 1.0, 20)
+
+
+@pytest.mark.parametrize("case", synth.PROJECT_CASES, ids=lambda c: c["name"])
+def test_project_oracle_matches_golden(case):
+    inp = synth.project_inputs(case)
+    got = project_oracle.project_scatter(inp["proj_matrix"], inp["pointcloud"], inp["labels"], case["H"], case["W"])
+    ref = load("project_%s.npz" % case["name"])
+    assert np.array_equal(got["rows"], ref["rows"]) and np.array_equal(got["cols"], ref["cols"])
+    assert np.array_equal(got["depth"], ref["feat"][0])
+    assert np.array_equal(np.moveaxis(got["xyzi"], -1, 0), ref["feat"][1:5])
+    assert np.array_equal(got["mask"].astype(np.float32), ref["mask"])
+    assert np.array_equal(got["label"].astype(np.float32), ref["label"])
+    assert np.array_equal(got["point_depth"], ref["depth"])
+    assert got["mask"].sum() > 100
+
+
+@pytest.mark.parametrize("case", synth.FUSION_CASES, ids=lambda c: c["name"])
+def test_fusion_oracle_matches_golden(case):
+    shapes = {}
+    pc, ic = case["pcd_c"], case["img_c"]
+    for name, cin in (("fuse_conv.0", pc + ic), ("attention.0", pc), ("attention.3", pc)):
+        shapes[name + ".weight"] = (pc, cin, 3, 3)
+        shapes[name + ".bias"] = (pc,)
+    for name in ("fuse_conv.2", "attention.1", "attention.4"):
+        for k, s in (("weight", (pc,)), ("bias", (pc,)), ("running_mean", (pc,)), ("running_var", (pc,)), ("num_batches_tracked", ())):
+            shapes[name + "." + k] = s
+    sd = po.synth_state_dict(shapes, seed=case["seed"])
+    sd = {"blk." + k: v for k, v in sd.items()}
+    pcd, img = synth.fusion_inputs(case)
+    ref = load("fusion_%s.npz" % case["name"])
+    out = po.fusion_block(po.Ctx(sd), pcd, img, "blk")
+    assert torch.allclose(out, torch.from_numpy(ref["out_eval"]), atol=1e-6, rtol=1e-6)
+    out = po.fusion_block(po.Ctx(sd, train=True), pcd, img, "blk")
+    assert torch.allclose(out, torch.from_numpy(ref["out_train"]), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("case", synth.PMF_CASES, ids=lambda c: c["name"])
+def test_pmf_oracle_matches_golden(case):
+    shapes = po.pmf_param_shapes(case["nclasses"], 32, case["backbone"])
+    sd = po.synth_state_dict(shapes, seed=case["seed"])
+    pcd, img = synth.pmf_inputs(case)
+    ref = load("pmf_%s.npz" % case["name"])
+    with torch.no_grad():
+        lid, cam = po.pmf_forward(sd, pcd, img, case["backbone"])
+    assert (lid - torch.from_numpy(ref["lidar_eval"])).abs().max() < 1e-6
+    assert (cam - torch.from_numpy(ref["camera_eval"])).abs().max() < 1e-6
+    params = {k: v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v for k, v in sd.items()}
+    lid, cam, ctx = po.pmf_forward(params, pcd, img, case["backbone"], train=True, return_ctx=True)
+    assert (lid - torch.from_numpy(ref["lidar_train"])).abs().max() < 1e-5
+    assert (cam - torch.from_numpy(ref["camera_train"])).abs().max() < 1e-5
+    wl, wc = synth.pmf_loss_weights(case)
+    loss = (lid * wl).sum() + (cam * wc).sum()
+    assert abs(loss.item() - float(ref["loss"])) < 1e-3 * max(1.0, abs(float(ref["loss"])))
+    loss.backward()
+    names = [str(n) for n in ref["grad_names"]]
+    for n, gn in zip(names, ref["grad_norms"]):
+        g = params[n].grad
+        assert g is not None
+        assert abs(float(g.double().norm()) - gn) <= 2e-3 * max(gn, 1e-6) + 1e-7, n
+    for n in synth.PMF_GRAD_PICKS:
+        g_ref = torch.from_numpy(ref["grad__" + n])
+        assert (params[n].grad - g_ref).abs().max() <= 2e-3 * g_ref.abs().max() + 1e-7, n
+    for k in synth.PMF_STAT_PICKS:
+        assert torch.allclose(ctx.new_stats[k], torch.from_numpy(ref["stat__" + k]), atol=1e-5, rtol=1e-5), k
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
+def test_oracle_equals_live_reference():
+    from oracle.ref_loader import load_reference
+    ref = load_reference()
+    torch.manual_seed(1)
+    m = ref.models.PMFNet(5, 3, 20, 32, False, "resnet34")
+    shapes = po.pmf_param_shapes(20, 32, "resnet34")
+    assert list(shapes.keys()) == list(m.state_dict().keys())
+    assert all(tuple(v.shape) == tuple(shapes[k]) for k, v in m.state_dict().items())
+    sd = m.state_dict()  # the reference's own default init
+    feat, _, _ = synth.frame_tensor(1, 16, 32, seed=5)
+    m.eval()
+    with torch.no_grad():
+        a, b = m(feat[:, :5], feat[:, 5:8])
+        a2, b2 = po.pmf_forward(sd, feat[:, :5], feat[:, 5:8])
+    assert torch.equal(a, a2) and torch.equal(b, b2)
+    # KNN: oracle vs the reference module on a fresh random case
+    case = dict(synth.KNN_CASES[0], seed=99, P=500)
+    inp = synth.knn_inputs(case)
+    knn = ref.postproc.KNN(dict(knn=5, search=5, sigma=1.0, cutoff=1.0), 20)
+    r = knn(*[torch.from_numpy(inp[k]) for k in ("proj_range", "unproj_range", "proj_argmax", "px", "py")]).numpy()
+    o, tf = knn_oracle.knn_vote(inp["proj_range"], inp["unproj_range"], inp["proj_argmax"], inp["px"], inp["py"], 5, 5, 1.0, 1.0, 20, return_aux=True)
+    assert np.array_equal(o[tf], r[tf])
