@@ -81,6 +81,8 @@ typedef struct {
   const float* w; /* packed [n_taps][c_out][c_in], c_in contiguous, values already tf32-rounded */
   int32_t c_in, c_out, n_taps;
   int32_t tap_dc[PMFB_MAX_TAPS], tap_dw[PMFB_MAX_TAPS], tap_dp[PMFB_MAX_TAPS], tap_dh[PMFB_MAX_TAPS];
+  int32_t tap_wi[PMFB_MAX_TAPS]; /* weight slab used by tap t (only if use_tap_wi; else slab t): lets the     */
+  int32_t use_tap_wi;            /* stride-2 dgrad run a SUBSET of the taps per input parity class            */
   int32_t n_batch, out_h, out_w; /* logical output grid                        */
   int32_t tile_w, tile_h;        /* tile_w*tile_h == 128 output pixels per CTA */
   int32_t n_tile;                /* output channels per CTA: multiple of 16, <= 256 */
@@ -111,6 +113,147 @@ int pmfb_init(void);
 
 int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream);
 int pmfb_conv_wgrad(const pmfb_wgrad_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout / packing kernels
+ * ------------------------------------------------------------------------------------------- */
+
+/* cudaMemsetAsync(ptr, 0, bytes) on the stream: zeroes the fp64 reduction scratch and the packed wgrad buffers. */
+int pmfb_memset_zero(void* ptr, size_t bytes, void* stream);
+
+/* NCHW-ish strided source (element strides s_n,s_c,s_h,s_w; e.g. the channel-slice views that
+ * tasks/pmf/trainer.py:296-297 passes) -> NHWC with c_dst channels at a pixel stride of dst_pix_stride
+ * elements (= c_dst for a dense tensor; larger when dst is a channel slice of a concat buffer):
+ *   dst[n,y,x, s*C + c] = src[n,c,y, x + s - n_shift/2]   (0 outside the row), s in [0,n_shift)
+ *   channels >= n_shift*C are zero.  n_shift=1: plain NCHW->NHWC (+channel zero-pad);
+ *   n_shift=7: the horizontally-unrolled input of the 7x7 stem (pmf_net.py:69-70), which turns the
+ *   7x7x3 convolution into a 7-tap (vertical) convolution over 21(+11 zero) channels on tcgen05.
+ * round_out: store tf32-rounded. */
+int pmfb_pack_input(const float* src, int64_t s_n, int64_t s_c, int64_t s_h, int64_t s_w, int32_t n, int32_t c,
+                    int32_t h, int32_t w, int32_t n_shift, float* dst, int32_t c_dst, int64_t dst_pix_stride,
+                    int32_t round_out, void* stream);
+
+/* dense NHWC view -> dense NCHW (module outputs, reference layout). */
+int pmfb_nhwc_to_nchw(const pmfb_view* src, int32_t n, int32_t h, int32_t w, int32_t c, float* dst, void* stream);
+
+/* OIHW conv weight -> packed tf32-rounded operands of the implicit GEMM, zero-padded to (c_out_p, c_in_p)
+ * (both multiples of 4, so 3/5/17-channel tensors become TMA-legal):
+ *   fwd  [taps][c_out_p][c_in_p]   (pmfb_conv_fwd forward)     if fwd   != NULL
+ *   dgrad[taps][c_in_p][c_out_p]   (pmfb_conv_fwd as dgrad)    if dgrad != NULL
+ * stem=1: the 7x7x3 stem; taps = kh and the packed input channel is kw_i*c_in + c (c_in_p >= kw*c_in). */
+int pmfb_pack_weight(const float* w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw, int32_t stem,
+                     int32_t c_out_p, int32_t c_in_p, float* fwd, float* dgrad, void* stream);
+
+/* packed wgrad [taps][c_in_p][c_out_p] -> OIHW gradient (grad = or += depending on accumulate). */
+int pmfb_unpack_wgrad(const float* packed, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw, int32_t stem,
+                      int32_t c_out_p, int32_t c_in_p, float* grad, int32_t accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Elementwise / normalisation kernels (NHWC views, C % 4 == 0)
+ * ------------------------------------------------------------------------------------------- */
+
+/* out = epilogue(in) elementwise; `in` may be NULL-ptr view meaning zeros.  Strides of 0 broadcast. */
+int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n, int32_t h,
+                   int32_t w, int32_t c, const pmfb_epilogue* epi, void* stream);
+
+/* sums[0:C] += sum_x, sums[C:2C] += sum_x^2 over all pixels (double accumulators, caller zeroes). */
+int pmfb_bn_stats(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, double* sums, void* stream);
+
+/* BatchNorm2d bookkeeping (nn.BatchNorm2d, eps 1e-5, momentum 0.1).
+ * train (sums != NULL): mean/var(biased) from sums over `count` elements; running stats updated in
+ *   place with the unbiased variance; eval (sums == NULL): uses running stats.
+ * Writes alpha = gamma*invstd, beta_out = beta - mean*alpha, and mean / invstd (for backward). */
+int pmfb_bn_finalize(const double* sums, int64_t count, int32_t c, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps, float* alpha,
+                     float* beta_out, float* mean_out, float* invstd_out, void* stream);
+
+/* BatchNorm / activation backward.  Common input gradient
+ *   g = dy * (mul.ptr ? mul : 1) * act'(z)        act_z in {NONE, RELU, LEAKY, SIGMOID}, derivative taken at the
+ *   OUTPUT z of the activation; if act_z != NONE and z.ptr == NULL, z is recomputed as act(alpha*x + beta)
+ *   (the sigmoid attention gate of pmf_net.py:20-35 is never stored).
+ * pass 1: red[0:C] += sum g, red[C:2C] += sum g*xhat, xhat = (x-mean)*invstd  (fp64, caller zeroes). */
+int pmfb_bn_bwd_reduce(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z,
+                       const pmfb_view* x, const float* mean, const float* invstd, const float* alpha,
+                       const float* beta, int32_t n, int32_t h, int32_t w, int32_t c, double* red, void* stream);
+
+/* pass 2:
+ *   mean != NULL:  dx = gamma*invstd*(g - S1/M - xhat*S2/M)       (BatchNorm backward, M = n*h*w)
+ *   mean == NULL:  dx = g                                          (plain activation backward)
+ *   leaky_x: dx *= (x > 0 ? 1 : 0.01)   (the conv->LeakyReLU->BN order of salsanext.py / pmf_net.py:13-18: x is
+ *            the stored activation output, whose sign is the pre-activation's sign)
+ *   dx (may be NULL) optionally tf32-rounded; dgamma = S2, dbeta = S1; colsum[0:C] += sum dx (bias gradient of
+ *   the preceding conv; fp64, caller zeroes) if colsum != NULL; if g_out != NULL, g is written (or accumulated)
+ *   there: the identity-branch gradient of a residual add. */
+int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z,
+                      const pmfb_view* x, const float* mean, const float* invstd, const float* alpha,
+                      const float* beta, const float* gamma, const double* red, int32_t leaky_x, int32_t n,
+                      int32_t h, int32_t w, int32_t c, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
+                      int32_t round_out, float* dgamma, float* dbeta, double* colsum, float* g_out, int64_t g_sn,
+                      int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* stream);
+
+/* out[i*C + c] (+)= sum over pixels (per image if per_image) of x; double accumulators, caller zeroes. */
+int pmfb_colsum(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t per_image, double* out,
+                void* stream);
+/* float dst = (or +=) (float)src * scale, n elements, optionally tf32-rounded. */
+int pmfb_d2f(const double* src, float* dst, int64_t n, float scale, int32_t accumulate, int32_t round_out,
+             void* stream);
+
+/* 3x3 stride-2 pad-1 pooling.  kind 0: AvgPool2d(count_include_pad) (salsanext.py:65);
+ * kind 1: MaxPool2d (torchvision stem), idx (uint8, dense [n,ho,wo,c]) records the arg-max tap 0..8.
+ * chan_scale (may be NULL): per-(n,c) Dropout2d scale applied to the pooled value (salsanext.py:92-96:
+ * pool(dropout(x)) == dropout-scale * pool(x) because the mask is constant over a plane). */
+int pmfb_pool3s2(int32_t kind, const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c,
+                 const float* chan_scale, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, uint8_t* idx,
+                 int32_t round_out, void* stream);
+int pmfb_pool3s2_bwd(int32_t kind, const pmfb_view* dy, int32_t n, int32_t h, int32_t w, int32_t c,
+                     const float* chan_scale, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
+                     const uint8_t* idx, int32_t accumulate, void* stream);
+
+/* PixelShuffle(2) (salsanext.py:137): out[n,2y+i,2x+j,c] = x[n,y,x,4c+2i+j] * (chan_scale ? chan_scale[n*C+c] : 1).
+ * (h,w,c) are the OUTPUT-side channel count c and INPUT spatial dims h,w.  bwd is the inverse gather. */
+int pmfb_pixel_shuffle(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, const float* chan_scale,
+                       float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t round_out, void* stream);
+int pmfb_pixel_shuffle_bwd(const pmfb_view* dy, int32_t n, int32_t h, int32_t w, int32_t c,
+                           const float* chan_scale, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
+                           int32_t accumulate, int32_t round_out, void* stream);
+
+/* nn.Upsample(scale_factor=2, mode="bilinear"), align_corners=False (pmf_net.py:191-210). (h,w) = input dims. */
+int pmfb_upsample2x(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, float* out, int64_t o_sn,
+                    int64_t o_sy, int64_t o_sx, int32_t round_out, void* stream);
+int pmfb_upsample2x_bwd(const pmfb_view* dy, int32_t n, int32_t h, int32_t w, int32_t c, float* dx, int64_t d_sn,
+                        int64_t d_sy, int64_t d_sx, int32_t accumulate, void* stream);
+
+/* F.softmax(dim=1) of NHWC logits, written as dense NCHW probabilities (pmf_net.py:177-178,221);
+ * bwd: dz[n,y,x,c] = p*(dp - sum_c dp*p) from dense NCHW p and dp.  c = number of classes (<= 64); the NHWC
+ * view holds c rounded up to a multiple of 4 channels, pad channels are ignored (fwd) / written as 0 (bwd). */
+int pmfb_softmax_nchw(const pmfb_view* logits, int32_t n, int32_t h, int32_t w, int32_t c, float* out, void* stream);
+int pmfb_softmax_nchw_bwd(const float* p, const float* dp, int32_t n, int32_t h, int32_t w, int32_t c, float* dz,
+                          int64_t d_sn, int64_t d_sy, int64_t d_sx, int32_t round_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Post-processing / pre-processing
+ * ------------------------------------------------------------------------------------------- */
+
+/* KNN.forward (pc_processor/postproc/knn.py:55-143): per point, S x S window of the range image
+ * (zero padded), |range - r| * (1 - gaussian) weights, k smallest (ties -> lower window index),
+ * cutoff -> class nclasses, vote over classes 1..nclasses-1, first max wins.
+ * inv_gauss: S*S fp32 table (1 - normalised gaussian), computed by the host exactly as knn.py:12-34.
+ * proj_argmax / px / py / out are int64 as the reference passes them. px = column, py = row. */
+int pmfb_knn_vote(const float* proj_range, const int64_t* proj_argmax, int32_t h, int32_t w,
+                  const float* unproj_range, const int64_t* px, const int64_t* py, int64_t n_points,
+                  const float* inv_gauss, int32_t search, int32_t knn, float cutoff, int32_t nclasses,
+                  int64_t* out, void* stream);
+
+/* Perspective projection + scatter (parser.py:209-227, perspective_view_loader.py:87-131):
+ * q = M*[x y z 1]^T in float64, keep x>0.5 and 0<u<W, 0<v<H, truncate to (row,col); per pixel the point
+ * with the HIGHEST index wins (numpy fancy-assignment order).  Two passes over `winner` (int32 H*W,
+ * caller provides; filled with -1 by this call).  feat: dense (5,H,W) [depth,x,y,z,i]; mask (H,W) f32;
+ * label_img (H,W) f32; rows/cols (N) int32 (-1 for dropped points); depth (N) f32 = |xyz|.
+ * points: device (N,4) fp32, 16-byte aligned; labels: device int32 (may be NULL);
+ * proj_matrix: HOST pointer to the 3x4 row-major float64 P2*Tr (it is passed by value to the kernel). */
+int pmfb_project_scatter(const float* points, const int32_t* labels, int64_t n_points, const double* proj_matrix,
+                         int32_t h, int32_t w, int32_t* winner, float* feat, float* mask, float* label_img,
+                         int32_t* rows, int32_t* cols, float* depth, void* stream);
 
 #ifdef __cplusplus
 }

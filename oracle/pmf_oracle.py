@@ -23,16 +23,33 @@ RESNET_LAYERS = {"resnet34": (3, 4, 6, 3), "resnet50": (3, 4, 6, 3), "resnet101"
 RESNET_EXPANSION = {"resnet34": 1, "resnet50": 4, "resnet101": 4, "resnet152": 4}
 
 
+def round_tf32(x):
+    """Round-to-nearest (ties away from zero) to the 10-bit tf32 mantissa, i.e. PTX cvt.rna.tf32.f32, as a
+    differentiable straight-through op.  Used only by the optional tensor-core EMULATION mode below."""
+    with torch.no_grad():
+        bits = x.detach().contiguous().view(torch.int32)
+        r = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    return x + (r - x).detach()
+
+
 class Ctx:
-    def __init__(self, sd, train=False, dropout=None):
+    """tf32=False (default): the reference's fp32 arithmetic (this is what is pinned to the reference).
+    tf32=True: conv operands (input and weight) are rounded to tf32 before every convolution, accumulation stays
+    fp32 — an emulation of the tcgen05 kind::tf32 path that lets tests separate indexing bugs (O(1) errors) from
+    the expected operand-rounding noise."""
+
+    def __init__(self, sd, train=False, dropout=None, tf32=False):
         self.sd = sd
         self.train = train
         self.dropout = dropout or {}
         self.new_stats = {}
+        self.tf32 = tf32
 
     def conv(self, x, name, stride=1, padding=0, dilation=1):
-        return F.conv2d(x, self.sd[name + ".weight"], self.sd.get(name + ".bias"), stride=stride,
-                        padding=padding, dilation=dilation)
+        w = self.sd[name + ".weight"]
+        if self.tf32:
+            x, w = round_tf32(x), round_tf32(w)
+        return F.conv2d(x, w, self.sd.get(name + ".bias"), stride=stride, padding=padding, dilation=dilation)
 
     def bn(self, x, name):
         w, b = self.sd[name + ".weight"], self.sd[name + ".bias"]
@@ -192,9 +209,10 @@ def rgb_decoder(c, feats, p):
     return F.softmax(c.conv(u1, p + ".conv", padding=1), dim=1)
 
 
-def pmf_forward(sd, pcd_feature, img_feature, backbone="resnet34", train=False, dropout=None, return_ctx=False):
+def pmf_forward(sd, pcd_feature, img_feature, backbone="resnet34", train=False, dropout=None, return_ctx=False,
+                tf32=False):
     """PMFNet.forward, pmf_net.py:242-249 -> (lidar_pred, camera_pred) softmax maps."""
-    c = Ctx(sd, train=train, dropout=dropout)
+    c = Ctx(sd, train=train, dropout=dropout, tf32=tf32)
     feats = resnet_encoder(c, img_feature, "camera_stream_encoder", backbone)
     lidar = salsanext_fusion(c, pcd_feature, feats, "lidar_stream")
     camera = rgb_decoder(c, feats, "camera_stream_decoder")

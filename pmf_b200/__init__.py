@@ -1,0 +1,10 @@
+"""pmf_b200 — B200-native (sm_100a) implementation of the ICEORY/PMF data-parallel hot path.
+
+Public surface (mirrors the reference's names):
+    pmf_b200.PMFNet, pmf_b200.ResidualBasedFusionBlock      pc_processor/models/pmf_net.py
+    pmf_b200.KNN                                            pc_processor/postproc/knn.py
+    pmf_b200.project_scatter                                perspective projection (parser.py:209-227 + loader scatter)
+Everything computes through libpmf_b200.so (include/pmfb.h); there is no CPU path.
+"""
+from .modules import PMFNet, ResidualBasedFusionBlock  # noqa: F401
+from .postproc import KNN, project_scatter  # noqa: F401

@@ -1,0 +1,137 @@
+"""ctypes binding of libpmf_b200.so (C-ABI declared in include/pmfb.h).
+
+The library is the product; there is no fallback.  If the shared object is missing, or a compute entry point is
+called without an sm_100 device, a RuntimeError carrying ``pmfb_last_error()`` is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpmf_b200.so")
+ABI_VERSION = 1
+MAX_TAPS = 9
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
+
+f32p = C.c_void_p  # raw device pointers are passed as integers
+i32, i64 = C.c_int32, C.c_int64
+
+
+class View(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("sn", i64), ("sy", i64), ("sx", i64)]
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("alpha1", C.c_void_p), ("beta1", C.c_void_p), ("alpha2", C.c_void_p), ("beta2", C.c_void_p),
+                ("r1", View), ("mul", View), ("r2", View), ("act", i32), ("round_out", i32)]
+
+
+class TmaSrc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dims", C.c_uint64 * 5), ("strides", C.c_uint64 * 4)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("x", TmaSrc), ("w", C.c_void_p), ("c_in", i32), ("c_out", i32), ("n_taps", i32),
+                ("tap_dc", i32 * MAX_TAPS), ("tap_dw", i32 * MAX_TAPS), ("tap_dp", i32 * MAX_TAPS),
+                ("tap_dh", i32 * MAX_TAPS), ("tap_wi", i32 * MAX_TAPS), ("use_tap_wi", i32), ("n_batch", i32),
+                ("out_h", i32), ("out_w", i32), ("tile_w", i32),
+                ("tile_h", i32), ("n_tile", i32), ("out", C.c_void_p), ("o_sn", i64), ("o_sy", i64), ("o_sx", i64),
+                ("epi", Epilogue)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("x", TmaSrc), ("dy", TmaSrc), ("c_in", i32), ("c_out", i32), ("n_taps", i32),
+                ("tap_dc", i32 * MAX_TAPS), ("tap_dw", i32 * MAX_TAPS), ("tap_dp", i32 * MAX_TAPS),
+                ("tap_dh", i32 * MAX_TAPS), ("n_batch", i32), ("out_h", i32), ("out_w", i32), ("ptile_w", i32),
+                ("ptile_h", i32), ("n_tile", i32), ("ksplit", i32), ("dw", C.c_void_p)]
+
+
+VP = C.POINTER(View)
+vp = C.c_void_p
+
+_SIGNATURES = {
+    "pmfb_abi_version": ([], C.c_int),
+    "pmfb_last_error": ([], C.c_char_p),
+    "pmfb_init": ([], C.c_int),
+    "pmfb_conv_fwd": ([C.POINTER(ConvDesc), vp], C.c_int),
+    "pmfb_conv_wgrad": ([C.POINTER(WgradDesc), vp], C.c_int),
+    "pmfb_memset_zero": ([vp, C.c_size_t, vp], C.c_int),
+    "pmfb_pack_input": ([vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, vp, i32, i64, i32, vp], C.c_int),
+    "pmfb_nhwc_to_nchw": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
+    "pmfb_pack_weight": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp], C.c_int),
+    "pmfb_unpack_wgrad": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp], C.c_int),
+    "pmfb_pointwise": ([VP, vp, i64, i64, i64, i32, i32, i32, i32, C.POINTER(Epilogue), vp], C.c_int),
+    "pmfb_bn_stats": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
+    "pmfb_bn_finalize": ([vp, i64, i32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp], C.c_int),
+    "pmfb_bn_bwd_reduce": ([VP, VP, VP, i32, VP, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp], C.c_int),
+    "pmfb_bn_bwd_apply": ([VP, VP, VP, i32, VP, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i64, i64, i64,
+                           i32, vp, vp, vp, vp, i64, i64, i64, i32, vp], C.c_int),
+    "pmfb_colsum": ([VP, i32, i32, i32, i32, i32, vp, vp], C.c_int),
+    "pmfb_d2f": ([vp, vp, i64, C.c_float, i32, i32, vp], C.c_int),
+    "pmfb_pool3s2": ([i32, VP, i32, i32, i32, i32, vp, vp, i64, i64, i64, vp, i32, vp], C.c_int),
+    "pmfb_pool3s2_bwd": ([i32, VP, i32, i32, i32, i32, vp, vp, i64, i64, i64, vp, i32, vp], C.c_int),
+    "pmfb_pixel_shuffle": ([VP, i32, i32, i32, i32, vp, vp, i64, i64, i64, i32, vp], C.c_int),
+    "pmfb_pixel_shuffle_bwd": ([VP, i32, i32, i32, i32, vp, vp, i64, i64, i64, i32, i32, vp], C.c_int),
+    "pmfb_upsample2x": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
+    "pmfb_upsample2x_bwd": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
+    "pmfb_softmax_nchw": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
+    "pmfb_softmax_nchw_bwd": ([vp, vp, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
+    "pmfb_knn_vote": ([vp, vp, i32, i32, vp, vp, vp, i64, vp, i32, i32, C.c_float, i32, vp, vp], C.c_int),
+    "pmfb_project_scatter": ([vp, vp, i64, C.POINTER(C.c_double), i32, i32, vp, vp, vp, vp, vp, vp, vp, vp], C.c_int),
+}
+
+EXPORTS = tuple(_SIGNATURES.keys())
+
+_lib = None
+launches = 0  # number of C-ABI compute calls issued (each enqueues >= 1 kernel); read by bench.py
+
+
+class PmfbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libpmf_b200.so (once).  Fails loudly when the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PmfbError("libpmf_b200.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "or `make -C pmf_b200/csrc` — there is no CPU fallback" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        if l.pmfb_abi_version() != ABI_VERSION:
+            raise PmfbError("libpmf_b200.so ABI %d != binding ABI %d" % (l.pmfb_abi_version(), ABI_VERSION))
+        _lib = l
+    return _lib
+
+
+def last_error():
+    return lib().pmfb_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = last_error()
+        if what == "pmfb_knn_vote" and "odd number" in msg:
+            raise ValueError(msg)  # knn.py:73-74 raises ValueError
+        raise PmfbError("%s failed (%d): %s" % (what, rc, msg))
+
+
+def call(name, *args):
+    global launches
+    launches += 1
+    check(getattr(lib(), name)(*args), name)
+
+
+_inited = False
+
+
+def require_device():
+    """pmfb_init(): an sm_100 device must be present."""
+    global _inited
+    if not _inited:
+        check(lib().pmfb_init(), "pmfb_init")
+        _inited = True

@@ -38,7 +38,7 @@ struct Ctrl {
 
 struct ConvFwdK {
   int n_taps, kc_per_tap;
-  int tap_dc[PMFB_MAX_TAPS], tap_dw[PMFB_MAX_TAPS], tap_dp[PMFB_MAX_TAPS], tap_dh[PMFB_MAX_TAPS];
+  int tap_dc[PMFB_MAX_TAPS], tap_dw[PMFB_MAX_TAPS], tap_dp[PMFB_MAX_TAPS], tap_dh[PMFB_MAX_TAPS], tap_wi[PMFB_MAX_TAPS];
   int tile_w, tile_h, tiles_x, tiles_y;
   int out_h, out_w, c_out, n_tile;
   int stages, tmem_cols;
@@ -102,7 +102,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
         mbar_expect_tx(&ctrl->full[s], (uint32_t)stage_bytes);
         tma_load_5d(a_s, &tmx, &ctrl->full[s], P.tap_dc[tap] + kc * 32, x0 + P.tap_dw[tap],
                     P.tap_dp[tap], y0 + P.tap_dh[tap], n_img);
-        tma_load_3d(b_s, &tmw, &ctrl->full[s], kc * 32, n0, tap);
+        tma_load_3d(b_s, &tmw, &ctrl->full[s], kc * 32, n0, P.tap_wi[tap]);
       }
     }
   } else if (warp == 1) {
@@ -322,7 +322,13 @@ extern "C" int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream) {
   uint32_t boxx[5] = {32, (uint32_t)d->tile_w, 1, (uint32_t)d->tile_h, 1};
   int rc = make_tmap_f32(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, boxx);
   if (rc) return rc;
-  uint64_t wdims[3] = {(uint64_t)d->c_in, (uint64_t)d->c_out, (uint64_t)d->n_taps};
+  int n_slabs = d->n_taps;
+  if (d->use_tap_wi)
+    for (int i = 0; i < d->n_taps; ++i) {
+      if (d->tap_wi[i] < 0) return fail(PMFB_ERR_INVALID, "tap_wi[%d]=%d", i, d->tap_wi[i]);
+      if (d->tap_wi[i] + 1 > n_slabs) n_slabs = d->tap_wi[i] + 1;
+    }
+  uint64_t wdims[3] = {(uint64_t)d->c_in, (uint64_t)d->c_out, (uint64_t)n_slabs};
   uint64_t wstr[2] = {(uint64_t)d->c_in * 4, (uint64_t)d->c_in * d->c_out * 4};
   uint32_t boxw[3] = {32, (uint32_t)d->n_tile, 1};
   rc = make_tmap_f32(&tmw, d->w, 3, wdims, wstr, boxw);
@@ -336,6 +342,7 @@ extern "C" int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream) {
     P.tap_dw[i] = d->tap_dw[i];
     P.tap_dp[i] = d->tap_dp[i];
     P.tap_dh[i] = d->tap_dh[i];
+    P.tap_wi[i] = d->use_tap_wi ? d->tap_wi[i] : i;
   }
   P.tile_w = d->tile_w;
   P.tile_h = d->tile_h;

@@ -1,0 +1,698 @@
+// Layout, packing and elementwise kernels of libpmf_b200.so (all HBM-bound; fp32 NHWC views, float4 per thread).
+//
+// Reference semantics being replaced (ATen kernels on the reference side):
+//   pointwise        : the BN-apply / activation / residual / gate chains of salsanext.py:23-36,69-104,136-164,
+//                      pmf_net.py:31-36 and torchvision BasicBlock
+//   pool3s2          : nn.AvgPool2d(3,2,1) salsanext.py:65 and nn.MaxPool2d(3,2,1) of the torchvision stem (pmf_net.py:95)
+//   pixel_shuffle    : nn.PixelShuffle(2) salsanext.py:137
+//   upsample2x       : nn.Upsample(scale_factor=2, mode="bilinear") pmf_net.py:191-210
+//   softmax_nchw     : F.softmax(dim=1) pmf_net.py:177-178,221
+#include "common.h"
+#include "epilogue.cuh"
+
+namespace pmfb {
+
+static inline int grid_for(long long work, int threads, int max_blocks = 148 * 16) {
+  long long b = (work + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+static inline bool view_ok(const pmfb_view* v) {
+  return !v->ptr || ((((v->sn | v->sy | v->sx) % 4) == 0) && ((reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0));
+}
+static inline bool out_ok(const float* p, int64_t sn, int64_t sy, int64_t sx) {
+  return p && (((sn | sy | sx) % 4) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+}
+
+__device__ __forceinline__ float4 rnd4(float4 v) {
+  v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------ pointwise
+__global__ void __launch_bounds__(256)
+pointwise_kernel(EpiView in, float* out, long long o_sn, long long o_sy, long long o_sx, int n, int h, int w, int c4,
+                 EpiParams E) {
+  const long long total = (long long)n * h * w * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    long long p = i / c4;
+    const int x = (int)(p % w);
+    p /= w;
+    const int y = (int)(p % h);
+    const int ni = (int)(p / h);
+    const int c = cg * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in.p) v = ld4(in.p + (long long)ni * in.sn + (long long)y * in.sy + (long long)x * in.sx + c);
+    EpiPixel ep = epi_pixel(E, ni, y, x);
+    v = epi_apply4(E, ep, c, v);
+    *reinterpret_cast<float4*>(out + (long long)ni * o_sn + (long long)y * o_sy + (long long)x * o_sx + c) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------ pack_input
+// one thread per destination pixel; reads are coalesced along x per source channel.
+__global__ void __launch_bounds__(256)
+pack_input_kernel(const float* __restrict__ src, long long s_n, long long s_c, long long s_h, long long s_w, int n, int c,
+                  int h, int w, int n_shift, float* __restrict__ dst, int c_dst, long long dst_pix_stride, int round_out) {
+  const long long total = (long long)n * h * w;
+  const int half = n_shift / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long p = i;
+    const int x = (int)(p % w);
+    p /= w;
+    const int y = (int)(p % h);
+    const int ni = (int)(p / h);
+    const float* s0 = src + (long long)ni * s_n + (long long)y * s_h;
+    float* d = dst + i * dst_pix_stride;
+    for (int j0 = 0; j0 < c_dst; j0 += 4) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = j0 + k;
+        float val = 0.f;
+        if (j < n_shift * c) {
+          const int s = j / c, ch = j - s * c;
+          const int xs = x + s - half;
+          if (xs >= 0 && xs < w) val = __ldg(s0 + (long long)ch * s_c + (long long)xs * s_w);
+        }
+        v[k] = round_out ? round_tf32(val) : val;
+      }
+      *reinterpret_cast<float4*>(d + j0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ NHWC -> NCHW
+// 32 pixels x 32 channels tile through shared memory.
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(EpiView src, int n, int h, int w, int c, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const long long hw = (long long)h * w;
+  const long long ptiles = (hw + 31) / 32;
+  const int ctiles = (c + 31) / 32;
+  const long long total = (long long)n * ptiles * ctiles;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int ct = (int)(t % ctiles);
+    long long r = t / ctiles;
+    const long long pt = r % ptiles;
+    const int ni = (int)(r / ptiles);
+    for (int k = threadIdx.x; k < 1024; k += 256) {
+      const int pl = k >> 5, cl = k & 31;
+      const long long p = pt * 32 + pl;
+      const int ch = ct * 32 + cl;
+      float v = 0.f;
+      if (p < hw && ch < c) {
+        const int y = (int)(p / w), x = (int)(p % w);
+        v = __ldg(src.p + (long long)ni * src.sn + (long long)y * src.sy + (long long)x * src.sx + ch);
+      }
+      tile[pl][cl] = v;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 1024; k += 256) {
+      const int cl = k >> 5, pl = k & 31;
+      const long long p = pt * 32 + pl;
+      const int ch = ct * 32 + cl;
+      if (p < hw && ch < c) dst[((long long)ni * c + ch) * hw + p] = tile[pl][cl];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------ weights
+// OIHW -> packed [taps][c_out_p][c_in_p] (fwd) and [taps][c_in_p][c_out_p] (dgrad); pad entries are zero.
+// stem: taps = kh, packed input channel j = kw_i*c_in + c (the horizontally unrolled 7x7 stem).
+__global__ void pack_weight_kernel(const float* __restrict__ w, int c_out, int c_in, int kh, int kw, int stem, int c_out_p,
+                                   int c_in_p, float* __restrict__ fwd, float* __restrict__ dgrad) {
+  const int taps = stem ? kh : kh * kw;
+  const long long total = (long long)taps * c_out_p * c_in_p;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % c_in_p);
+    long long r = i / c_in_p;
+    const int co = (int)(r % c_out_p);
+    const int t = (int)(r / c_out_p);
+    float v = 0.f;
+    if (co < c_out) {
+      if (stem) {
+        if (j < kw * c_in) {
+          const int kj = j / c_in, ci = j - kj * c_in;
+          v = w[(((long long)co * c_in + ci) * kh + t) * kw + kj];
+        }
+      } else if (j < c_in) {
+        v = w[((long long)co * c_in + j) * taps + t];
+      }
+    }
+    v = round_tf32(v);
+    if (fwd) fwd[i] = v;
+    if (dgrad) dgrad[((long long)t * c_in_p + j) * c_out_p + co] = v;
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int c_out, int c_in, int kh, int kw, int stem,
+                                    int c_out_p, int c_in_p, float* __restrict__ grad, int accumulate) {
+  const int taps = kh * kw;
+  const long long total = (long long)c_out * c_in * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    long long r = i / taps;
+    const int ci = (int)(r % c_in);
+    const int co = (int)(r / c_in);
+    float v;
+    if (stem) {
+      const int ki = t / kw, kj = t - ki * kw;
+      v = packed[((long long)ki * c_in_p + (kj * c_in + ci)) * c_out_p + co];
+    } else {
+      v = packed[((long long)t * c_in_p + ci) * c_out_p + co];
+    }
+    grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+
+__global__ void d2f_kernel(const double* __restrict__ src, float* __restrict__ dst, long long n, float scale, int accumulate,
+                           int round_out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = (float)(src[i] * (double)scale);
+    if (accumulate) v += dst[i];
+    dst[i] = round_out ? round_tf32(v) : v;
+  }
+}
+
+// ------------------------------------------------------------------------------------ 3x3 s2 p1 pooling
+__global__ void __launch_bounds__(256)
+pool3s2_kernel(int kind, EpiView xin, int n, int h, int w, int c4, const float* __restrict__ chan_scale, float* out,
+               long long o_sn, long long o_sy, long long o_sx, uint8_t* idx, int round_out) {
+  const int ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * ho * wo * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    long long p = i / c4;
+    const int xo = (int)(p % wo);
+    p /= wo;
+    const int yo = (int)(p % ho);
+    const int ni = (int)(p / ho);
+    const int c = cg * 4;
+    float4 acc;
+    uchar4 am = make_uchar4(0, 0, 0, 0);
+    if (kind == 0) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    else acc = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int y = 2 * yo - 1 + t / 3, x = 2 * xo - 1 + t % 3;
+      if (y < 0 || y >= h || x < 0 || x >= w) continue;
+      const float4 v = ld4(xin.p + (long long)ni * xin.sn + (long long)y * xin.sy + (long long)x * xin.sx + c);
+      if (kind == 0) {
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      } else {
+        if (v.x > acc.x) { acc.x = v.x; am.x = t; }
+        if (v.y > acc.y) { acc.y = v.y; am.y = t; }
+        if (v.z > acc.z) { acc.z = v.z; am.z = t; }
+        if (v.w > acc.w) { acc.w = v.w; am.w = t; }
+      }
+    }
+    if (kind == 0) {
+      acc.x /= 9.f; acc.y /= 9.f; acc.z /= 9.f; acc.w /= 9.f;
+    } else if (idx) {
+      *reinterpret_cast<uchar4*>(idx + (((long long)ni * ho + yo) * wo + xo) * (c4 * 4) + c) = am;
+    }
+    if (chan_scale) {
+      const float4 sc = ld4(chan_scale + (long long)ni * (c4 * 4) + c);
+      acc.x *= sc.x; acc.y *= sc.y; acc.z *= sc.z; acc.w *= sc.w;
+    }
+    if (round_out) acc = rnd4(acc);
+    *reinterpret_cast<float4*>(out + (long long)ni * o_sn + (long long)yo * o_sy + (long long)xo * o_sx + c) = acc;
+  }
+}
+
+// gather form: every input pixel sums the (at most 4) output windows that cover it.
+__global__ void __launch_bounds__(256)
+pool3s2_bwd_kernel(int kind, EpiView dy, int n, int h, int w, int c4, const float* __restrict__ chan_scale, float* dx,
+                   long long d_sn, long long d_sy, long long d_sx, const uint8_t* __restrict__ idx, int accumulate) {
+  const int ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * h * w * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    long long p = i / c4;
+    const int x = (int)(p % w);
+    p /= w;
+    const int y = (int)(p % h);
+    const int ni = (int)(p / h);
+    const int c = cg * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // windows: 2*yo-1 <= y <= 2*yo+1  ->  yo in [ceil((y-1)/2), floor((y+1)/2)]
+    const int yo_lo = y / 2, yo_hi = (y + 1) / 2;
+    const int xo_lo = x / 2, xo_hi = (x + 1) / 2;
+    for (int yo = yo_lo; yo <= yo_hi; ++yo) {
+      if (yo >= ho) continue;
+      for (int xo = xo_lo; xo <= xo_hi; ++xo) {
+        if (xo >= wo) continue;
+        const float4 g = ld4(dy.p + (long long)ni * dy.sn + (long long)yo * dy.sy + (long long)xo * dy.sx + c);
+        if (kind == 0) {
+          acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        } else {
+          const int t = (y - (2 * yo - 1)) * 3 + (x - (2 * xo - 1));
+          const uchar4 am = *reinterpret_cast<const uchar4*>(idx + (((long long)ni * ho + yo) * wo + xo) * (c4 * 4) + c);
+          if (am.x == t) acc.x += g.x;
+          if (am.y == t) acc.y += g.y;
+          if (am.z == t) acc.z += g.z;
+          if (am.w == t) acc.w += g.w;
+        }
+      }
+    }
+    if (kind == 0) {
+      acc.x /= 9.f; acc.y /= 9.f; acc.z /= 9.f; acc.w /= 9.f;
+    }
+    if (chan_scale) {
+      const float4 sc = ld4(chan_scale + (long long)ni * (c4 * 4) + c);
+      acc.x *= sc.x; acc.y *= sc.y; acc.z *= sc.z; acc.w *= sc.w;
+    }
+    float* d = dx + (long long)ni * d_sn + (long long)y * d_sy + (long long)x * d_sx + c;
+    if (accumulate) {
+      const float4 o = *reinterpret_cast<const float4*>(d);
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    *reinterpret_cast<float4*>(d) = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------ PixelShuffle(2)
+// thread = (input pixel, group of 4 OUTPUT channels): reads 16 contiguous input channels, writes 4 pixels x float4.
+__global__ void __launch_bounds__(256)
+pixel_shuffle_kernel(EpiView xin, int n, int h, int w, int c4, const float* __restrict__ chan_scale, float* out,
+                     long long o_sn, long long o_sy, long long o_sx, int round_out) {
+  const long long total = (long long)n * h * w * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    long long p = i / c4;
+    const int x = (int)(p % w);
+    p /= w;
+    const int y = (int)(p % h);
+    const int ni = (int)(p / h);
+    const float* s = xin.p + (long long)ni * xin.sn + (long long)y * xin.sy + (long long)x * xin.sx + cg * 16;
+    const float4 a = ld4(s), b = ld4(s + 4), cc = ld4(s + 8), d = ld4(s + 12);  // channel 4*(4cg+k) + 2i+j
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (chan_scale) sc = ld4(chan_scale + (long long)ni * (c4 * 4) + cg * 4);
+    float4 o[4];
+    o[0] = make_float4(a.x * sc.x, b.x * sc.y, cc.x * sc.z, d.x * sc.w);
+    o[1] = make_float4(a.y * sc.x, b.y * sc.y, cc.y * sc.z, d.y * sc.w);
+    o[2] = make_float4(a.z * sc.x, b.z * sc.y, cc.z * sc.z, d.z * sc.w);
+    o[3] = make_float4(a.w * sc.x, b.w * sc.y, cc.w * sc.z, d.w * sc.w);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ii = q >> 1, jj = q & 1;
+      float4 v = round_out ? rnd4(o[q]) : o[q];
+      *reinterpret_cast<float4*>(out + (long long)ni * o_sn + (long long)(2 * y + ii) * o_sy + (long long)(2 * x + jj) * o_sx +
+                                 cg * 4) = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pixel_shuffle_bwd_kernel(EpiView dy, int n, int h, int w, int c4, const float* __restrict__ chan_scale, float* dx,
+                         long long d_sn, long long d_sy, long long d_sx, int accumulate, int round_out) {
+  const long long total = (long long)n * h * w * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    long long p = i / c4;
+    const int x = (int)(p % w);
+    p /= w;
+    const int y = (int)(p % h);
+    const int ni = (int)(p / h);
+    float4 g[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ii = q >> 1, jj = q & 1;
+      g[q] = ld4(dy.p + (long long)ni * dy.sn + (long long)(2 * y + ii) * dy.sy + (long long)(2 * x + jj) * dy.sx + cg * 4);
+    }
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (chan_scale) sc = ld4(chan_scale + (long long)ni * (c4 * 4) + cg * 4);
+    float4 o[4];
+    o[0] = make_float4(g[0].x * sc.x, g[1].x * sc.x, g[2].x * sc.x, g[3].x * sc.x);
+    o[1] = make_float4(g[0].y * sc.y, g[1].y * sc.y, g[2].y * sc.y, g[3].y * sc.y);
+    o[2] = make_float4(g[0].z * sc.z, g[1].z * sc.z, g[2].z * sc.z, g[3].z * sc.z);
+    o[3] = make_float4(g[0].w * sc.w, g[1].w * sc.w, g[2].w * sc.w, g[3].w * sc.w);
+    float* d = dx + (long long)ni * d_sn + (long long)y * d_sy + (long long)x * d_sx + cg * 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 v = o[k];
+      if (accumulate) {
+        const float4 e = *reinterpret_cast<const float4*>(d + 4 * k);
+        v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+      }
+      if (round_out) v = rnd4(v);
+      *reinterpret_cast<float4*>(d + 4 * k) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ bilinear x2 (align_corners=False)
+__device__ __forceinline__ void up2_src(int o, int size, int& i0, int& i1, float& l1) {
+  float s = 0.5f * (o + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  i1 = i0 + (i0 < size - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(EpiView xin, int n, int h, int w, int c4, float* out, long long o_sn, long long o_sy, long long o_sx,
+                  int round_out) {
+  const int ho = 2 * h, wo = 2 * w;
+  const long long total = (long long)n * ho * wo * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    long long p = i / c4;
+    const int xo = (int)(p % wo);
+    p /= wo;
+    const int yo = (int)(p % ho);
+    const int ni = (int)(p / ho);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    up2_src(yo, h, y0, y1, ly);
+    up2_src(xo, w, x0, x1, lx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* b = xin.p + (long long)ni * xin.sn + cg * 4;
+    const float4 v00 = ld4(b + (long long)y0 * xin.sy + (long long)x0 * xin.sx);
+    const float4 v01 = ld4(b + (long long)y0 * xin.sy + (long long)x1 * xin.sx);
+    const float4 v10 = ld4(b + (long long)y1 * xin.sy + (long long)x0 * xin.sx);
+    const float4 v11 = ld4(b + (long long)y1 * xin.sy + (long long)x1 * xin.sx);
+    float4 o;
+    o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+    o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+    o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
+    o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+    if (round_out) o = rnd4(o);
+    *reinterpret_cast<float4*>(out + (long long)ni * o_sn + (long long)yo * o_sy + (long long)xo * o_sx + cg * 4) = o;
+  }
+}
+
+__device__ __forceinline__ float up2_weight(int o, int size, int i) {
+  int i0, i1;
+  float l1;
+  up2_src(o, size, i0, i1, l1);
+  float wgt = 0.f;
+  if (i0 == i) wgt += 1.f - l1;
+  if (i1 == i) wgt += l1;
+  return wgt;
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(EpiView dy, int n, int h, int w, int c4, float* dx, long long d_sn, long long d_sy, long long d_sx,
+                      int accumulate) {
+  const int ho = 2 * h, wo = 2 * w;
+  const long long total = (long long)n * h * w * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    long long p = i / c4;
+    const int x = (int)(p % w);
+    p /= w;
+    const int y = (int)(p % h);
+    const int ni = (int)(p / h);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int yo = 2 * y - 1; yo <= 2 * y + 2; ++yo) {
+      if (yo < 0 || yo >= ho) continue;
+      const float wy = up2_weight(yo, h, y);
+      if (wy == 0.f) continue;
+      for (int xo = 2 * x - 1; xo <= 2 * x + 2; ++xo) {
+        if (xo < 0 || xo >= wo) continue;
+        const float wgt = wy * up2_weight(xo, w, x);
+        if (wgt == 0.f) continue;
+        const float4 g = ld4(dy.p + (long long)ni * dy.sn + (long long)yo * dy.sy + (long long)xo * dy.sx + cg * 4);
+        acc.x += wgt * g.x; acc.y += wgt * g.y; acc.z += wgt * g.z; acc.w += wgt * g.w;
+      }
+    }
+    float* d = dx + (long long)ni * d_sn + (long long)y * d_sy + (long long)x * d_sx + cg * 4;
+    if (accumulate) {
+      const float4 e = *reinterpret_cast<const float4*>(d);
+      acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
+    }
+    *reinterpret_cast<float4*>(d) = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------ softmax over channels
+// one thread per pixel; NHWC logits in, dense NCHW probabilities out (plane writes are coalesced across the warp).
+constexpr int kMaxSoftmaxC = 64;
+
+__global__ void __launch_bounds__(256)
+softmax_nchw_kernel(EpiView lg, int n, int h, int w, int c, float* __restrict__ out) {
+  const long long hw = (long long)h * w;
+  const long long total = (long long)n * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ni = (int)(i / hw);
+    const long long p = i - (long long)ni * hw;
+    const int y = (int)(p / w), x = (int)(p % w);
+    const float* s = lg.p + (long long)ni * lg.sn + (long long)y * lg.sy + (long long)x * lg.sx;
+    float v[kMaxSoftmaxC];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kMaxSoftmaxC; j += 4) {
+      if (j < c) {  // the view is padded to a multiple of 4 channels; pad lanes are ignored
+        const float4 t = ld4(s + j);
+        v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxSoftmaxC; ++j)
+      if (j < c) m = fmaxf(m, v[j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxSoftmaxC; ++j) {
+      if (j < c) {
+        v[j] = expf(v[j] - m);
+        sum += v[j];
+      }
+    }
+    const float inv = 1.f / sum;
+    float* o = out + (long long)ni * c * hw + p;
+#pragma unroll
+    for (int j = 0; j < kMaxSoftmaxC; ++j)
+      if (j < c) o[(long long)j * hw] = v[j] * inv;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+softmax_nchw_bwd_kernel(const float* __restrict__ pr, const float* __restrict__ dp, int n, int h, int w, int c, float* dz,
+                        long long d_sn, long long d_sy, long long d_sx, int round_out) {
+  const long long hw = (long long)h * w;
+  const long long total = (long long)n * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ni = (int)(i / hw);
+    const long long p = i - (long long)ni * hw;
+    const int y = (int)(p / w), x = (int)(p % w);
+    const float* pp = pr + (long long)ni * c * hw + p;
+    const float* gp = dp + (long long)ni * c * hw + p;
+    float pv[kMaxSoftmaxC], gv[kMaxSoftmaxC];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxSoftmaxC; ++j) {
+      if (j < c) {
+        pv[j] = __ldg(pp + (long long)j * hw);
+        gv[j] = __ldg(gp + (long long)j * hw);
+        dot += pv[j] * gv[j];
+      }
+    }
+    float* d = dz + (long long)ni * d_sn + (long long)y * d_sy + (long long)x * d_sx;
+#pragma unroll
+    for (int j = 0; j < kMaxSoftmaxC; j += 4) {
+      if (j < c) {
+        float4 o = make_float4(pv[j] * (gv[j] - dot), j + 1 < c ? pv[j + 1] * (gv[j + 1] - dot) : 0.f,
+                               j + 2 < c ? pv[j + 2] * (gv[j + 2] - dot) : 0.f,
+                               j + 3 < c ? pv[j + 3] * (gv[j + 3] - dot) : 0.f);
+        if (round_out) o = rnd4(o);
+        *reinterpret_cast<float4*>(d + j) = o;
+      }
+    }
+  }
+}
+
+static inline EpiView ev(const pmfb_view* v) {
+  EpiView e;
+  e.p = v ? v->ptr : nullptr;
+  e.sn = v ? v->sn : 0;
+  e.sy = v ? v->sy : 0;
+  e.sx = v ? v->sx : 0;
+  return e;
+}
+
+}  // namespace pmfb
+
+using namespace pmfb;
+
+#define REQ(cond, ...) \
+  do {                 \
+    if (!(cond)) return fail(PMFB_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+extern "C" int pmfb_memset_zero(void* ptr, size_t bytes, void* stream) {
+  REQ(ptr || bytes == 0, "memset_zero: null pointer");
+  if (bytes == 0) return PMFB_OK;
+  PMFB_CUDA_CHECK(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream));
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n,
+                              int32_t h, int32_t w, int32_t c, const pmfb_epilogue* epi, void* stream) {
+  REQ(epi && c > 0 && c % 4 == 0, "pointwise: c=%d must be a positive multiple of 4", c);
+  REQ(out_ok(out, o_sn, o_sy, o_sx), "pointwise: bad output view");
+  REQ(!in || view_ok(in), "pointwise: bad input view");
+  EpiParams E;
+  int rc = epi_from_c(epi, &E);
+  if (rc) return rc;
+  const long long total = (long long)n * h * w * (c / 4);
+  if (total == 0) return PMFB_OK;
+  pointwise_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(in), out, o_sn, o_sy, o_sx, n, h, w, c / 4, E);
+  PMFB_LAUNCH_CHECK("pointwise_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_pack_input(const float* src, int64_t s_n, int64_t s_c, int64_t s_h, int64_t s_w, int32_t n, int32_t c,
+                               int32_t h, int32_t w, int32_t n_shift, float* dst, int32_t c_dst, int64_t dst_pix_stride,
+                               int32_t round_out, void* stream) {
+  REQ(src && dst && c > 0 && n_shift >= 1 && (n_shift & 1), "pack_input: bad arguments");
+  REQ(c_dst % 4 == 0 && c_dst >= n_shift * c, "pack_input: c_dst=%d must be a multiple of 4 and >= %d", c_dst, n_shift * c);
+  REQ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && dst_pix_stride >= c_dst && dst_pix_stride % 4 == 0,
+      "pack_input: dst must be 16-byte aligned with a pixel stride >= c_dst that is a multiple of 4");
+  const long long total = (long long)n * h * w;
+  if (total == 0) return PMFB_OK;
+  pack_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, s_n, s_c, s_h, s_w, n, c, h, w, n_shift, dst,
+                                                                            c_dst, dst_pix_stride, round_out);
+  PMFB_LAUNCH_CHECK("pack_input_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_nhwc_to_nchw(const pmfb_view* src, int32_t n, int32_t h, int32_t w, int32_t c, float* dst, void* stream) {
+  REQ(src && src->ptr && dst && c > 0, "nhwc_to_nchw: bad arguments");
+  const long long tiles = (long long)n * (((long long)h * w + 31) / 32) * ((c + 31) / 32);
+  if (tiles == 0) return PMFB_OK;
+  nhwc_to_nchw_kernel<<<(int)(tiles < 148 * 16 ? tiles : 148 * 16), 256, 0, (cudaStream_t)stream>>>(ev(src), n, h, w, c, dst);
+  PMFB_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_pack_weight(const float* w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw, int32_t stem,
+                                int32_t c_out_p, int32_t c_in_p, float* fwd, float* dgrad, void* stream) {
+  REQ(w && (fwd || dgrad) && c_out > 0 && c_in > 0 && kh > 0 && kw > 0, "pack_weight: bad arguments");
+  REQ(c_out_p >= c_out && c_out_p % 4 == 0 && c_in_p % 4 == 0 && c_in_p >= (stem ? kw * c_in : c_in),
+      "pack_weight: padded dims (%d,%d) too small or not multiples of 4", c_out_p, c_in_p);
+  const long long total = (long long)(stem ? kh : kh * kw) * c_out_p * c_in_p;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, c_out, c_in, kh, kw, stem, c_out_p, c_in_p, fwd,
+                                                                             dgrad);
+  PMFB_LAUNCH_CHECK("pack_weight_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_unpack_wgrad(const float* packed, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw, int32_t stem,
+                                 int32_t c_out_p, int32_t c_in_p, float* grad, int32_t accumulate, void* stream) {
+  REQ(packed && grad && c_out > 0 && c_in > 0, "unpack_wgrad: bad arguments");
+  REQ(c_out_p >= c_out && c_in_p >= (stem ? kw * c_in : c_in), "unpack_wgrad: padded dims too small");
+  const long long total = (long long)c_out * c_in * kh * kw;
+  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, c_out, c_in, kh, kw, stem, c_out_p, c_in_p,
+                                                                              grad, accumulate);
+  PMFB_LAUNCH_CHECK("unpack_wgrad_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_d2f(const double* src, float* dst, int64_t n, float scale, int32_t accumulate, int32_t round_out,
+                        void* stream) {
+  REQ(src && dst && n >= 0, "d2f: bad arguments");
+  if (n == 0) return PMFB_OK;
+  d2f_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n, scale, accumulate, round_out);
+  PMFB_LAUNCH_CHECK("d2f_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_pool3s2(int32_t kind, const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c,
+                            const float* chan_scale, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, uint8_t* idx,
+                            int32_t round_out, void* stream) {
+  REQ(x && x->ptr && view_ok(x) && out_ok(out, o_sn, o_sy, o_sx), "pool3s2: bad views");
+  REQ(c % 4 == 0 && h % 2 == 0 && w % 2 == 0 && (kind == 0 || kind == 1), "pool3s2: c%%4, even h/w, kind in {0,1}");
+  const long long total = (long long)n * (h / 2) * (w / 2) * (c / 4);
+  if (total == 0) return PMFB_OK;
+  pool3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(kind, ev(x), n, h, w, c / 4, chan_scale, out, o_sn, o_sy,
+                                                                         o_sx, idx, round_out);
+  PMFB_LAUNCH_CHECK("pool3s2_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_pool3s2_bwd(int32_t kind, const pmfb_view* dy, int32_t n, int32_t h, int32_t w, int32_t c,
+                                const float* chan_scale, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
+                                const uint8_t* idx, int32_t accumulate, void* stream) {
+  REQ(dy && dy->ptr && view_ok(dy) && out_ok(dx, d_sn, d_sy, d_sx), "pool3s2_bwd: bad views");
+  REQ(c % 4 == 0 && h % 2 == 0 && w % 2 == 0 && (kind == 0 || (kind == 1 && idx)), "pool3s2_bwd: bad arguments");
+  const long long total = (long long)n * h * w * (c / 4);
+  if (total == 0) return PMFB_OK;
+  pool3s2_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(kind, ev(dy), n, h, w, c / 4, chan_scale, dx, d_sn, d_sy,
+                                                                             d_sx, idx, accumulate);
+  PMFB_LAUNCH_CHECK("pool3s2_bwd_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_pixel_shuffle(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, const float* chan_scale,
+                                  float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t round_out, void* stream) {
+  REQ(x && x->ptr && view_ok(x) && out_ok(out, o_sn, o_sy, o_sx) && c % 4 == 0, "pixel_shuffle: bad arguments");
+  const long long total = (long long)n * h * w * (c / 4);
+  if (total == 0) return PMFB_OK;
+  pixel_shuffle_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(x), n, h, w, c / 4, chan_scale, out, o_sn, o_sy,
+                                                                               o_sx, round_out);
+  PMFB_LAUNCH_CHECK("pixel_shuffle_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_pixel_shuffle_bwd(const pmfb_view* dy, int32_t n, int32_t h, int32_t w, int32_t c,
+                                      const float* chan_scale, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
+                                      int32_t accumulate, int32_t round_out, void* stream) {
+  REQ(dy && dy->ptr && view_ok(dy) && out_ok(dx, d_sn, d_sy, d_sx) && c % 4 == 0, "pixel_shuffle_bwd: bad arguments");
+  const long long total = (long long)n * h * w * (c / 4);
+  if (total == 0) return PMFB_OK;
+  pixel_shuffle_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(dy), n, h, w, c / 4, chan_scale, dx, d_sn,
+                                                                                   d_sy, d_sx, accumulate, round_out);
+  PMFB_LAUNCH_CHECK("pixel_shuffle_bwd_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_upsample2x(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, float* out, int64_t o_sn,
+                               int64_t o_sy, int64_t o_sx, int32_t round_out, void* stream) {
+  REQ(x && x->ptr && view_ok(x) && out_ok(out, o_sn, o_sy, o_sx) && c % 4 == 0, "upsample2x: bad arguments");
+  const long long total = (long long)n * (2 * h) * (2 * w) * (c / 4);
+  if (total == 0) return PMFB_OK;
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(x), n, h, w, c / 4, out, o_sn, o_sy, o_sx,
+                                                                            round_out);
+  PMFB_LAUNCH_CHECK("upsample2x_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_upsample2x_bwd(const pmfb_view* dy, int32_t n, int32_t h, int32_t w, int32_t c, float* dx, int64_t d_sn,
+                                   int64_t d_sy, int64_t d_sx, int32_t accumulate, void* stream) {
+  REQ(dy && dy->ptr && view_ok(dy) && out_ok(dx, d_sn, d_sy, d_sx) && c % 4 == 0, "upsample2x_bwd: bad arguments");
+  const long long total = (long long)n * h * w * (c / 4);
+  if (total == 0) return PMFB_OK;
+  upsample2x_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(dy), n, h, w, c / 4, dx, d_sn, d_sy, d_sx,
+                                                                                accumulate);
+  PMFB_LAUNCH_CHECK("upsample2x_bwd_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_softmax_nchw(const pmfb_view* logits, int32_t n, int32_t h, int32_t w, int32_t c, float* out,
+                                 void* stream) {
+  REQ(logits && logits->ptr && view_ok(logits) && out, "softmax_nchw: bad views");
+  REQ(c > 0 && c <= kMaxSoftmaxC, "softmax_nchw: c=%d must be in [1,%d]", c, kMaxSoftmaxC);
+  const long long total = (long long)n * h * w;
+  if (total == 0) return PMFB_OK;
+  softmax_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(logits), n, h, w, c, out);
+  PMFB_LAUNCH_CHECK("softmax_nchw_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_softmax_nchw_bwd(const float* p, const float* dp, int32_t n, int32_t h, int32_t w, int32_t c, float* dz,
+                                     int64_t d_sn, int64_t d_sy, int64_t d_sx, int32_t round_out, void* stream) {
+  REQ(p && dp && out_ok(dz, d_sn, d_sy, d_sx), "softmax_nchw_bwd: bad views");
+  REQ(c > 0 && c <= kMaxSoftmaxC, "softmax_nchw_bwd: c=%d must be in [1,%d]", c, kMaxSoftmaxC);
+  const long long total = (long long)n * h * w;
+  if (total == 0) return PMFB_OK;
+  softmax_nchw_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p, dp, n, h, w, c, dz, d_sn, d_sy, d_sx,
+                                                                                  round_out);
+  PMFB_LAUNCH_CHECK("softmax_nchw_bwd_kernel");
+  return PMFB_OK;
+}

@@ -1,0 +1,737 @@
+"""Host-side executor for the PMF hot path: NHWC fp32 activations in HBM, every device op a C-ABI call into
+libpmf_b200.so (no torch compute kernels on the path; torch only owns the memory and the stream).
+
+The executor keeps its own backward tape (one closure per fused op) instead of using torch.autograd per op:
+gradients are written straight into channel slices of shared concat buffers (``torch.cat`` never materialises),
+accumulation is folded into the producing kernel's epilogue, and tf32 rounding of conv operands happens where a
+tensor is produced.  ``pmf_b200.modules`` wraps one whole forward/backward in a single autograd.Function.
+
+Reference semantics (paths relative to the reference tree):
+  conv_act      nn.Conv2d -> LeakyReLU / identity          salsanext.py:24-25,70-71; pmf_net.py:106-117; salsanext.py:186
+  conv_act_bn   nn.Conv2d -> LeakyReLU -> BatchNorm2d       salsanext.py:27-33,73-90,145-160; pmf_net.py:13-18,187-209
+  conv_bn       nn.Conv2d -> BatchNorm2d -> ReLU/Sigmoid    torchvision BasicBlock/Bottleneck; pmf_net.py:20-29,35
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ConvDesc, Epilogue, TmaSrc, View, WgradDesc
+
+BN_EPS_DEFAULT = 1e-5
+N_SM = 148
+
+
+def _rup(x, m):
+    return (x + m - 1) // m * m
+
+
+def _view(t):
+    """ctypes View of an NHWC torch view (N,H,W,C) with channel stride 1, or None -> null view."""
+    v = View()
+    if t is None:
+        v.ptr, v.sn, v.sy, v.sx = None, 0, 0, 0
+        return v
+    assert t.dim() == 4 and (t.shape[3] == 1 or t.stride(3) == 1), (t.shape, t.stride())
+    v.ptr, v.sn, v.sy, v.sx = t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)
+    v._keep = t
+    return v
+
+
+def _chan_view(m):
+    """(N,C) per-image channel scale (Dropout2d mask) as a broadcasting NHWC view."""
+    v = View()
+    v.ptr, v.sn, v.sy, v.sx = m.data_ptr(), m.stride(0), 0, 0
+    v._keep = m  # the View travels into backward closures: keep the mask's storage alive with it
+    return v
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class Act:
+    """An NHWC activation: ``t`` is a (N,H,W,C) torch view; slices share the root's gradient buffer."""
+    __slots__ = ("t", "root", "c0", "needs_grad", "_round_grad", "grad", "gcov")
+
+    def __init__(self, t, root=None, c0=0, needs_grad=True):
+        self.t = t
+        self.root = root if root is not None else self
+        self.c0 = c0
+        self.needs_grad = needs_grad
+        self._round_grad = False  # root only; see round_grad
+        self.grad = None         # root only: dense NHWC gradient buffer
+        self.gcov = []           # root only: channel intervals of grad already written
+
+    @property
+    def shape(self):
+        return tuple(self.t.shape)
+
+    @property
+    def c(self):
+        return self.t.shape[3]
+
+    @property
+    def round_grad(self):
+        """True when some producer's backward feeds this buffer's gradient straight into a tensor-core conv:
+        every writer of the gradient then stores tf32-rounded values."""
+        return self.root._round_grad
+
+    @round_grad.setter
+    def round_grad(self, v):
+        self.root._round_grad = bool(v)
+
+    def slice(self, a, b):
+        s = Act(self.t[..., a:b], root=self.root, c0=self.c0 + a, needs_grad=self.root.needs_grad)
+        return s
+
+    # ---- gradient bookkeeping -------------------------------------------------------------------------
+    def _cov_state(self, a, b):
+        covered = 0
+        for (x, y) in self.root.gcov:
+            lo, hi = max(a, x), min(b, y)
+            if hi > lo:
+                covered += hi - lo
+        return "full" if covered == b - a else ("none" if covered == 0 else "partial")
+
+    def _cov_add(self, a, b):
+        iv = sorted(self.root.gcov + [(a, b)])
+        merged = [iv[0]]
+        for (x, y) in iv[1:]:
+            if x <= merged[-1][1]:
+                merged[-1] = (merged[-1][0], max(merged[-1][1], y))
+            else:
+                merged.append((x, y))
+        self.root.gcov = merged
+
+    def grad_target(self):
+        """(grad view, accumulate?) for a writer of this activation's gradient."""
+        r = self.root
+        if r.grad is None:
+            r.grad = torch.empty(r.t.shape, device=r.t.device, dtype=torch.float32)
+        a, b = self.c0, self.c0 + self.c
+        st = self._cov_state(a, b)
+        g = r.grad[..., a:b]
+        if st == "partial":  # rare: zero the unwritten channels, then accumulate everywhere
+            pos = a
+            for (x, y) in r.gcov + [(b, b)]:
+                lo, hi = max(pos, a), min(x, b)
+                if hi > lo:
+                    L.call("pmfb_pointwise", None, r.grad[..., lo:hi].data_ptr(), r.grad.stride(0), r.grad.stride(1),
+                           r.grad.stride(2), r.t.shape[0], r.t.shape[1], r.t.shape[2], hi - lo, C.byref(Epilogue()),
+                           torch.cuda.current_stream().cuda_stream)
+                pos = max(pos, y)
+            self._cov_add(a, b)
+            return g, True
+        if st == "none":
+            self._cov_add(a, b)
+            return g, False
+        return g, True
+
+    def grad_read(self):
+        r = self.root
+        a, b = self.c0, self.c0 + self.c
+        if r.grad is None or self._cov_state(a, b) != "full":
+            raise RuntimeError("gradient of an activation was requested before every consumer produced it")
+        return r.grad[..., a:b]
+
+
+class ConvParam:
+    """Geometry + live parameter tensors of one nn.Conv2d."""
+    __slots__ = ("name", "weight", "bias", "c_out", "c_in", "kh", "kw", "dil", "pad", "stride", "stem", "c_out_p",
+                 "c_in_p")
+
+    def __init__(self, name, weight, bias, dil, pad, stride, stem=False):
+        self.name = name
+        self.weight, self.bias = weight, bias
+        self.c_out, self.c_in, self.kh, self.kw = weight.shape
+        self.dil, self.pad, self.stride, self.stem = dil, pad, stride, stem
+        self.c_out_p = _rup(self.c_out, 4)
+        self.c_in_p = 32 if stem else _rup(self.c_in, 4)
+
+    @property
+    def taps(self):
+        return self.kh if self.stem else self.kh * self.kw
+
+    def fwd_taps(self):
+        """[(dc, dw, dp, dh, weight_tap)] of the forward implicit GEMM."""
+        out = []
+        if self.stem:
+            for i in range(self.kh):
+                out.append((0, 0, 0, i - self.pad, i))
+            return out
+        for i in range(self.kh):
+            for j in range(self.kw):
+                dh, dw = i * self.dil - self.pad, j * self.dil - self.pad
+                if self.stride == 1:
+                    out.append((0, dw, 0, dh, i * self.kw + j))
+                else:  # input viewed as (2C, W/2, 2, H/2, N): every tap is a plain box
+                    ph, pw = dh % 2, dw % 2
+                    out.append((pw * self.c_in_p, (dw - pw) // 2, ph, (dh - ph) // 2, i * self.kw + j))
+        return out
+
+
+class BNParam:
+    __slots__ = ("name", "weight", "bias", "running_mean", "running_var", "nbt", "momentum", "eps", "c")
+
+    def __init__(self, name, mod):
+        self.name = name
+        self.weight, self.bias = mod.weight, mod.bias
+        self.running_mean, self.running_var = mod.running_mean, mod.running_var
+        self.nbt = getattr(mod, "num_batches_tracked", None)
+        self.momentum = 0.1 if mod.momentum is None else float(mod.momentum)
+        self.eps = float(mod.eps)
+        self.c = mod.weight.shape[0]
+
+
+def _pick_tile(h, w, total):
+    best = None
+    tw = total
+    while tw >= 1:
+        th = total // tw
+        cost = _rup(w, tw) * _rup(h, th)
+        if best is None or cost < best[0]:
+            best = (cost, tw, th)
+        tw //= 2
+    return best[1], best[2]
+
+
+class WeightCache:
+    """Packed tf32 copies of the conv weights, re-packed when the parameter's version or storage changes."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def get(self, cp, need_dgrad, stream):
+        w = cp.weight
+        key = cp.name
+        tag = (w.data_ptr(), w._version, None if cp.bias is None else (cp.bias.data_ptr(), cp.bias._version), need_dgrad)
+        e = self.entries.get(key)
+        if e is not None and e["tag"] == tag:
+            return e
+        dev = w.device
+        if e is None or e["fwd"].device != dev or (need_dgrad and e["dgrad"] is None):
+            e = {"fwd": torch.empty(cp.taps * cp.c_out_p * cp.c_in_p, device=dev, dtype=torch.float32),
+                 "dgrad": (torch.empty(cp.taps * cp.c_out_p * cp.c_in_p, device=dev, dtype=torch.float32)
+                           if need_dgrad else None),
+                 "bias": None}
+        wd = w.detach()
+        if not wd.is_contiguous():
+            wd = wd.contiguous()
+        L.call("pmfb_pack_weight", wd.data_ptr(), cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0, cp.c_out_p,
+               cp.c_in_p, e["fwd"].data_ptr(), _p(e["dgrad"]) if need_dgrad else None, stream)
+        if cp.bias is not None:
+            if cp.c_out_p != cp.c_out:
+                b = torch.zeros(cp.c_out_p, device=dev, dtype=torch.float32)
+                b[:cp.c_out] = cp.bias.detach()
+                e["bias"] = b
+            else:
+                e["bias"] = cp.bias.detach()
+        e["tag"] = tag
+        self.entries[key] = e
+        return e
+
+
+class _Scratch:
+    """Bump allocator over one zero-initialised buffer (fp64 reduction cells) or an uninitialised fp32 one."""
+
+    def __init__(self, dtype, n, device, stream, zero):
+        self.dtype, self.n, self.device, self.stream, self.zero = dtype, n, device, stream, zero
+        self.chunks = []
+        self._new_chunk()
+
+    def _new_chunk(self):
+        self.buf = torch.empty(self.n, device=self.device, dtype=self.dtype)
+        if self.zero:
+            L.call("pmfb_memset_zero", self.buf.data_ptr(), self.n * self.buf.element_size(), self.stream)
+        self.chunks.append(self.buf)
+        self.pos = 0
+
+    def take(self, k):
+        k4 = _rup(k, 4)
+        if self.pos + k4 > self.n:
+            self.n = max(self.n, k4)
+            self._new_chunk()
+        out = self.buf[self.pos:self.pos + k]
+        self.pos += k4
+        return out
+
+
+class Engine:
+    """One forward (and optionally backward) pass.  ``params``: object with conv(name)->ConvParam, bn(name)->BNParam."""
+
+    def __init__(self, params, device, train, record, cache, dropout=None):
+        L.require_device()
+        self.P = params
+        self.device = device
+        self.train = bool(train)
+        self.record = bool(record)
+        if self.record and not self.train:
+            raise NotImplementedError("pmf_b200: backward is implemented for train-mode (batch-statistics) BatchNorm only; "
+                                      "call .train() or run the eval forward under torch.no_grad()")
+        self.cache = cache
+        self.st = torch.cuda.current_stream(device).cuda_stream
+        self.tape = []
+        self.dropout = dropout  # see mask_for
+        self.d64 = _Scratch(torch.float64, 1 << 17, device, self.st, zero=True)
+        self.f32 = _Scratch(torch.float32, 1 << 17, device, self.st, zero=False)
+        self.param_grads = {}
+        self.nbt_list = []
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def new(self, n, h, w, c, needs_grad=True):
+        return Act(torch.empty((n, h, w, c), device=self.device, dtype=torch.float32), needs_grad=needs_grad)
+
+    def _epi(self, alpha1=None, beta1=None, alpha2=None, beta2=None, r1=None, mul=None, r2=None, act=ACT_NONE, rnd=0):
+        e = Epilogue()
+        e.alpha1, e.beta1, e.alpha2, e.beta2 = _p(alpha1), _p(beta1), _p(alpha2), _p(beta2)
+        for name, v in (("r1", r1), ("mul", mul), ("r2", r2)):
+            if v is None:
+                continue
+            setattr(e, name, v if isinstance(v, View) else _view(v))
+        e.act, e.round_out = act, rnd
+        return e
+
+    def pointwise(self, src, dst, **kw):
+        """dst = epilogue(src) elementwise; src None means zeros; src may be a View (broadcast)."""
+        n, h, w, c = dst.shape
+        e = self._epi(**kw)
+        sv = src if isinstance(src, View) else _view(src)
+        L.call("pmfb_pointwise", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
+               C.byref(e), self.st)
+
+    def mask_for(self, site, n, c):
+        """Dropout2d scale per (image, channel): 0 or 1/(1-p); None when the site is inactive.
+        ``self.dropout``: False = off; dict = explicit {site: (N,C) mask}; otherwise an object with
+        draw(site, n, c, device) (pmf_b200.modules._DropoutSites: torch RNG, honours per-module .eval())."""
+        if self.dropout is False or self.dropout is None or not self.train:
+            return None
+        if hasattr(self.dropout, "draw"):
+            return self.dropout.draw(site, n, c, self.device)
+        m = self.dropout.get(site)
+        if m is None:
+            return None
+        return m.to(device=self.device, dtype=torch.float32).reshape(n, c).contiguous()
+
+    # ------------------------------------------------------------------------------------------ inputs / outputs
+    def input_nchw(self, x, c_pad, n_shift=1, out=None, needs_grad=False, rnd=True):
+        """NCHW (possibly strided) torch tensor -> NHWC Act (tf32-rounded, channel padded)."""
+        n, c, h, w = x.shape
+        if out is None:
+            out = self.new(n, h, w, c_pad, needs_grad=needs_grad)
+        assert out.t.stride(1) == w * out.t.stride(2) and out.t.stride(0) == h * out.t.stride(1)
+        xd = x.detach()
+        if xd.dtype != torch.float32:
+            xd = xd.float()
+        L.call("pmfb_pack_input", xd.data_ptr(), xd.stride(0), xd.stride(1), xd.stride(2), xd.stride(3), n, c, h, w, n_shift,
+               out.t.data_ptr(), out.c, out.t.stride(2), 1 if rnd else 0, self.st)
+        return out
+
+    def to_nchw(self, t, c):
+        """NHWC view (first c channels) -> dense NCHW torch tensor."""
+        n, h, w, _ = t.shape
+        out = torch.empty((n, c, h, w), device=self.device, dtype=torch.float32)
+        L.call("pmfb_nhwc_to_nchw", C.byref(_view(t)), n, h, w, c, out.data_ptr(), self.st)
+        return out
+
+    # ------------------------------------------------------------------------------------------ raw conv launches
+    @staticmethod
+    def _tma_src(t, c, stride2=False):
+        """TmaSrc over an NHWC view; c = channels exposed to the kernel (zero-filled beyond)."""
+        s = TmaSrc()
+        n, h, w, _ = t.shape
+        sn, sy, sx = t.stride(0), t.stride(1), t.stride(2)
+        s.ptr = t.data_ptr()
+        if not stride2:
+            s.dims[:] = [c, w, 1, h, n]
+            s.strides[:] = [sx * 4, sy * 4, sy * 4, sn * 4]
+        else:
+            assert sx == c and h % 2 == 0 and w % 2 == 0, "stride-2 convs need a dense NHWC input"
+            s.dims[:] = [2 * c, w // 2, 2, h // 2, n]
+            s.strides[:] = [2 * sx * 4, sy * 4, 2 * sy * 4, sn * 4]
+        return s
+
+    def _conv_launch(self, x_t, c_in, stride2, w_packed, c_out, taps, n, out_h, out_w, out_t, epi):
+        d = ConvDesc()
+        d.x = self._tma_src(x_t, c_in, stride2)
+        d.w = w_packed.data_ptr()
+        d.c_in, d.c_out, d.n_taps = c_in, c_out, len(taps)
+        for i, (dc, dw, dp, dh, wi) in enumerate(taps):
+            d.tap_dc[i], d.tap_dw[i], d.tap_dp[i], d.tap_dh[i], d.tap_wi[i] = dc, dw, dp, dh, wi
+        d.use_tap_wi = 1
+        d.n_batch, d.out_h, d.out_w = n, out_h, out_w
+        d.tile_w, d.tile_h = _pick_tile(out_h, out_w, 128)
+        d.n_tile = min(256, _rup(c_out, 16))
+        d.out = out_t.data_ptr()
+        d.o_sn, d.o_sy, d.o_sx = out_t.stride(0), out_t.stride(1), out_t.stride(2)
+        d.epi = epi
+        L.call("pmfb_conv_fwd", C.byref(d), self.st)
+
+    def _conv_fwd(self, x, cp, out_t, epi):
+        """out = epi(conv(x)); x: Act whose channel count equals cp.c_in_p."""
+        e = self.cache.get(cp, self.record, self.st)
+        n, h, w, cx = x.shape
+        assert cx == cp.c_in_p, (cp.name, cx, cp.c_in_p)
+        if cp.stem:
+            oh, ow = h, w
+        else:
+            oh = (h + 2 * cp.pad - cp.dil * (cp.kh - 1) - 1) // cp.stride + 1
+            ow = (w + 2 * cp.pad - cp.dil * (cp.kw - 1) - 1) // cp.stride + 1
+        assert tuple(out_t.shape) == (n, oh, ow, cp.c_out_p), (cp.name, tuple(out_t.shape), (n, oh, ow, cp.c_out_p))
+        self._conv_launch(x.t, cp.c_in_p, cp.stride == 2, e["fwd"], cp.c_out_p, cp.fwd_taps(), n, oh, ow, out_t, epi)
+        return e
+
+    def _conv_bwd(self, x, cp, d_pre):
+        """wgrad (+ dgrad into x's gradient) of out = conv(x) given d_pre = dL/d(conv output), tf32-rounded."""
+        e = self.cache.get(cp, True, self.st)
+        n, h, w, _ = x.shape
+        _, oh, ow, co = d_pre.shape
+        assert co == cp.c_out_p
+        # ---- wgrad -> packed [taps][c_in_p][c_out_p] (split-K atomics; buffer zeroed here) -> OIHW
+        packed = torch.empty(cp.taps * cp.c_in_p * cp.c_out_p, device=self.device, dtype=torch.float32)
+        L.call("pmfb_memset_zero", packed.data_ptr(), packed.numel() * 4, self.st)
+        d = WgradDesc()
+        d.x = self._tma_src(x.t, cp.c_in_p, cp.stride == 2)
+        d.dy = self._tma_src(d_pre, cp.c_out_p)
+        d.c_in, d.c_out, d.n_taps = cp.c_in_p, cp.c_out_p, cp.taps
+        for i, (dc, dw, dp, dh, _wi) in enumerate(cp.fwd_taps()):
+            d.tap_dc[i], d.tap_dw[i], d.tap_dp[i], d.tap_dh[i] = dc, dw, dp, dh
+        d.n_batch, d.out_h, d.out_w = n, oh, ow
+        d.ptile_w, d.ptile_h = _pick_tile(oh, ow, 32)
+        d.n_tile = min(256, _rup(cp.c_out_p, 32))
+        total_pt = (_rup(ow, d.ptile_w) // d.ptile_w) * (_rup(oh, d.ptile_h) // d.ptile_h) * n
+        base = ((cp.taps * (_rup(cp.c_in_p, 32) // 32) + 3) // 4) * ((cp.c_out_p + d.n_tile - 1) // d.n_tile)
+        d.ksplit = max(1, min(max(1, total_pt // 4), (2 * N_SM + base - 1) // base))
+        d.dw = packed.data_ptr()
+        L.call("pmfb_conv_wgrad", C.byref(d), self.st)
+        gw = torch.empty_like(cp.weight, memory_format=torch.contiguous_format)
+        L.call("pmfb_unpack_wgrad", packed.data_ptr(), cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0, cp.c_out_p,
+               cp.c_in_p, gw.data_ptr(), 0, self.st)
+        self.param_grads[cp.name + ".weight"] = gw
+        # ---- dgrad
+        if not x.needs_grad:
+            return
+        assert not cp.stem and cp.c_in_p == cp.c_in
+        gx, acc = x.grad_target()
+        rnd = 1 if x.round_grad else 0
+        if cp.stride == 1:
+            taps = [(0, -dw, 0, -dh, wi) for (_dc, dw, _dp, dh, wi) in cp.fwd_taps()]
+            self._conv_launch(d_pre, cp.c_out_p, False, e["dgrad"], cp.c_in_p, taps, n, h, w, gx,
+                              self._epi(r1=gx if acc else None, rnd=rnd))
+            return
+        # stride 2: one stride-1 convolution over dy per input parity class
+        for py in (0, 1):
+            for px in (0, 1):
+                taps = []
+                for i in range(cp.kh):
+                    for j in range(cp.kw):
+                        dh, dw = i * cp.dil - cp.pad, j * cp.dil - cp.pad
+                        if (py - dh) % 2 == 0 and (px - dw) % 2 == 0:
+                            taps.append((0, (px - dw) // 2, 0, (py - dh) // 2, i * cp.kw + j))
+                sub = gx[:, py::2, px::2, :]
+                if not taps:
+                    if not acc:
+                        self.pointwise(None, sub)
+                    continue
+                self._conv_launch(d_pre, cp.c_out_p, False, e["dgrad"], cp.c_in_p, taps, n, h // 2, w // 2, sub,
+                                  self._epi(r1=sub if acc else None, rnd=rnd))
+
+    def _bias_grad(self, cp, colsum64):
+        gb = torch.empty_like(cp.bias)
+        L.call("pmfb_d2f", colsum64.data_ptr(), gb.data_ptr(), cp.c_out, 1.0, 0, 0, self.st)
+        self.param_grads[cp.name + ".bias"] = gb
+
+    # ------------------------------------------------------------------------------------------ BatchNorm pieces
+    def _bn_eval_affine(self, bn):
+        ab = self.f32.take(2 * bn.c)
+        alpha, beta = ab[:bn.c], ab[bn.c:]
+        L.call("pmfb_bn_finalize", None, 0, bn.c, _p(bn.weight.detach()), _p(bn.bias.detach()), bn.running_mean.data_ptr(),
+               bn.running_var.data_ptr(), bn.momentum, bn.eps, alpha.data_ptr(), beta.data_ptr(), None, None, self.st)
+        return alpha, beta
+
+    def _bn_train_affine(self, bn, a_t):
+        n, h, w, c = a_t.shape
+        assert c == bn.c
+        sums = self.d64.take(2 * c)
+        L.call("pmfb_bn_stats", C.byref(_view(a_t)), n, h, w, c, sums.data_ptr(), self.st)
+        v = self.f32.take(4 * c)
+        alpha, beta, mean, invstd = v[:c], v[c:2 * c], v[2 * c:3 * c], v[3 * c:]
+        L.call("pmfb_bn_finalize", sums.data_ptr(), n * h * w, c, _p(bn.weight.detach()), _p(bn.bias.detach()),
+               bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.momentum, bn.eps, alpha.data_ptr(), beta.data_ptr(),
+               mean.data_ptr(), invstd.data_ptr(), self.st)
+        if bn.nbt is not None:
+            self.nbt_list.append(bn.nbt)
+        return alpha, beta, mean, invstd
+
+    def _bn_backward(self, bn, dy, a_t, stats, mul=None, z=None, act_z=ACT_NONE, leaky_x=0, want_colsum=False,
+                     g_out=None, g_acc=False):
+        """Returns (d_pre [tf32-rounded gradient w.r.t. the conv output], colsum64 or None)."""
+        alpha, beta, mean, invstd = stats
+        n, h, w, c = a_t.shape
+        red = self.d64.take(2 * c)
+        dyv, mulv, zv, xv = _view(dy), (mul if isinstance(mul, View) else _view(mul)), _view(z), _view(a_t)
+        L.call("pmfb_bn_bwd_reduce", C.byref(dyv), C.byref(mulv), C.byref(zv), act_z, C.byref(xv), mean.data_ptr(),
+               invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), n, h, w, c, red.data_ptr(), self.st)
+        d_pre = torch.empty((n, h, w, c), device=self.device, dtype=torch.float32)
+        cs = self.d64.take(c) if want_colsum else None
+        gw, gb = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
+        L.call("pmfb_bn_bwd_apply", C.byref(dyv), C.byref(mulv), C.byref(zv), act_z, C.byref(xv), mean.data_ptr(),
+               invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), bn.weight.detach().data_ptr(), red.data_ptr(), leaky_x,
+               n, h, w, c, d_pre.data_ptr(), d_pre.stride(0), d_pre.stride(1), d_pre.stride(2), 1, gw.data_ptr(),
+               gb.data_ptr(), _p(cs), _p(g_out), *( (g_out.stride(0), g_out.stride(1), g_out.stride(2)) if g_out is not None
+                                                    else (0, 0, 0)), 1 if g_acc else 0, self.st)
+        self.param_grads[bn.name + ".weight"] = gw
+        self.param_grads[bn.name + ".bias"] = gb
+        return d_pre, cs
+
+    def _out_for(self, x, cp, out):
+        n, h, w, _ = x.shape
+        if cp.stem:
+            oh, ow = h, w
+        else:
+            oh = (h + 2 * cp.pad - cp.dil * (cp.kh - 1) - 1) // cp.stride + 1
+            ow = (w + 2 * cp.pad - cp.dil * (cp.kw - 1) - 1) // cp.stride + 1
+        if out is None:
+            out = self.new(n, oh, ow, cp.c_out_p)
+        return out, (n, oh, ow, cp.c_out_p)
+
+    # ------------------------------------------------------------------------------------------ fused layer patterns
+    def conv_act(self, x, cname, act=ACT_NONE, out=None, rnd=True):
+        """y = act(conv(x) + bias), act in {NONE, LEAKY}."""
+        cp = self.P.conv(cname)
+        y, _ = self._out_for(x, cp, out)
+        e = self.cache.get(cp, self.record, self.st)
+        self._conv_fwd(x, cp, y.t, self._epi(beta1=e["bias"], act=act, rnd=1 if rnd else 0))
+        if self.record:
+            if act == ACT_NONE:
+                y.round_grad = True
+
+            def bwd():
+                dy = y.grad_read()
+                n, h, w, c = dy.shape
+                cs = self.d64.take(c) if cp.bias is not None else None
+                if act == ACT_NONE:
+                    d_pre = dy
+                    if cs is not None:
+                        L.call("pmfb_colsum", C.byref(_view(dy)), n, h, w, c, 0, cs.data_ptr(), self.st)
+                else:
+                    d_pre = torch.empty((n, h, w, c), device=self.device, dtype=torch.float32)
+                    nv = View()
+                    L.call("pmfb_bn_bwd_apply", C.byref(_view(dy)), C.byref(nv), C.byref(_view(y.t)), act, C.byref(nv), None,
+                           None, None, None, None, None, 0, n, h, w, c, d_pre.data_ptr(), d_pre.stride(0), d_pre.stride(1),
+                           d_pre.stride(2), 1, None, None, _p(cs), None, 0, 0, 0, 0, self.st)
+                if cs is not None:
+                    self._bias_grad(cp, cs)
+                self._conv_bwd(x, cp, d_pre)
+
+            self.tape.append(bwd)
+        return y
+
+    def conv_act_bn(self, x, cname, bnname, out=None, shortcut=None, mask=None):
+        """y = (BN(LeakyReLU(conv(x) + bias)) + shortcut) * mask   (SalsaNext / fusion / decoder order)."""
+        cp, bn = self.P.conv(cname), self.P.bn(bnname)
+        y, shp = self._out_for(x, cp, out)
+        e = self.cache.get(cp, self.record, self.st)
+        sc_t = None if shortcut is None else shortcut.t
+        if not self.train:
+            alpha, beta = self._bn_eval_affine(bn)
+            self._conv_fwd(x, cp, y.t, self._epi(beta1=e["bias"], act=ACT_LEAKY, alpha2=alpha, beta2=beta, r2=sc_t, rnd=1))
+            return y
+        a = torch.empty(shp, device=self.device, dtype=torch.float32)
+        self._conv_fwd(x, cp, a, self._epi(beta1=e["bias"], act=ACT_LEAKY))
+        stats = self._bn_train_affine(bn, a)
+        mv = None if mask is None else _chan_view(mask)
+        self.pointwise(a, y.t, alpha1=stats[0], beta1=stats[1], r1=sc_t, mul=mv, rnd=1)
+        if self.record:
+            def bwd():
+                dy = y.grad_read()
+                g_out, g_acc = (None, False)
+                if shortcut is not None and shortcut.needs_grad:
+                    g_out, g_acc = shortcut.grad_target()
+                d_pre, cs = self._bn_backward(bn, dy, a, stats, mul=mv, leaky_x=1, want_colsum=cp.bias is not None,
+                                              g_out=g_out, g_acc=g_acc)
+                if cs is not None:
+                    self._bias_grad(cp, cs)
+                self._conv_bwd(x, cp, d_pre)
+
+            self.tape.append(bwd)
+        return y
+
+    def conv_bn(self, x, cname, bnname, post=ACT_NONE, out=None, identity=None, mask=None, gate=None, rnd=True):
+        """y = post(BN(conv(x) + bias) + identity) * mask          (torchvision blocks, attention.0/1/2)
+        gate=(f, pcd):  y = sigmoid(BN(conv(x) + bias)) * f + pcd    (attention.3/4/5 + pmf_net.py:35)."""
+        cp, bn = self.P.conv(cname), self.P.bn(bnname)
+        y, shp = self._out_for(x, cp, out)
+        e = self.cache.get(cp, self.record, self.st)
+        id_t = None if identity is None else identity.t
+        f_t, pcd_t = (gate[0].t, gate[1].t) if gate is not None else (None, None)
+        if not self.train:
+            alpha, beta = self._bn_eval_affine(bn)
+            if e["bias"] is not None:  # beta' = alpha*bias + beta  (tiny per-channel vector op on the device)
+                b2 = self.f32.take(bn.c)
+                self.pointwise(e["bias"].view(1, 1, 1, -1), b2.view(1, 1, 1, -1), alpha1=alpha, beta1=beta)
+                beta = b2
+            self._conv_fwd(x, cp, y.t, self._epi(alpha1=alpha, beta1=beta, r1=id_t, act=post, mul=f_t, r2=pcd_t,
+                                                 rnd=1 if rnd else 0))
+            return y
+        c_t = torch.empty(shp, device=self.device, dtype=torch.float32)
+        self._conv_fwd(x, cp, c_t, self._epi(beta1=e["bias"]))
+        stats = self._bn_train_affine(bn, c_t)
+        mv = None if mask is None else _chan_view(mask)
+        self.pointwise(c_t, y.t, alpha1=stats[0], beta1=stats[1], r1=id_t, act=post, mul=f_t if gate is not None else mv,
+                       r2=pcd_t, rnd=1 if rnd else 0)
+        if self.record:
+            def bwd():
+                dy = y.grad_read()
+                if gate is not None:
+                    f, pcd = gate
+                    gf, acc = f.grad_target()  # d f = dy * sigmoid(BN(c))
+                    self.pointwise(c_t, gf, alpha1=stats[0], beta1=stats[1], act=ACT_SIGMOID, mul=dy, r2=gf if acc else None)
+                    if pcd.needs_grad:
+                        gp, acc = pcd.grad_target()  # d pcd = dy
+                        self.pointwise(dy, gp, r1=gp if acc else None)
+                    d_pre, cs = self._bn_backward(bn, dy, c_t, stats, mul=f.t, z=None, act_z=ACT_SIGMOID,
+                                                  want_colsum=cp.bias is not None)
+                else:
+                    g_out, g_acc = (None, False)
+                    if identity is not None and identity.needs_grad:
+                        g_out, g_acc = identity.grad_target()
+                    d_pre, cs = self._bn_backward(bn, dy, c_t, stats, mul=mv, z=y.t if post != ACT_NONE else None, act_z=post,
+                                                  want_colsum=cp.bias is not None, g_out=g_out, g_acc=g_acc)
+                if cs is not None:
+                    self._bias_grad(cp, cs)
+                self._conv_bwd(x, cp, d_pre)
+
+            self.tape.append(bwd)
+        return y
+
+    # ------------------------------------------------------------------------------------------ data movement ops
+    def copy(self, src, dst, mask=None):
+        """dst = src * mask (a channel slice of a concat buffer)."""
+        mv = None if mask is None else _chan_view(mask)
+        self.pointwise(src.t, dst.t, mul=mv, rnd=1 if mask is not None else 0)
+        if self.record and src.needs_grad:
+            def bwd():
+                g = dst.grad_read()
+                gs, acc = src.grad_target()
+                self.pointwise(g, gs, mul=mv, r2=gs if acc else None, rnd=1 if src.round_grad else 0)
+
+            self.tape.append(bwd)
+        return dst
+
+    def pool(self, x, kind, out=None, mask=None):
+        """3x3 stride-2 pad-1 pooling; kind 'avg' (salsanext.py:65) or 'max' (torchvision stem)."""
+        n, h, w, c = x.shape
+        k = 0 if kind == "avg" else 1
+        if out is None:
+            out = self.new(n, h // 2, w // 2, c)
+        idx = torch.empty((n, h // 2, w // 2, c), device=self.device, dtype=torch.uint8) if (k == 1 and self.record) else None
+        L.call("pmfb_pool3s2", k, C.byref(_view(x.t)), n, h, w, c, _p(mask), out.t.data_ptr(), out.t.stride(0), out.t.stride(1),
+               out.t.stride(2), _p(idx), 1, self.st)
+        if self.record and x.needs_grad:
+            def bwd():
+                g = out.grad_read()
+                gx, acc = x.grad_target()
+                L.call("pmfb_pool3s2_bwd", k, C.byref(_view(g)), n, h, w, c, _p(mask), gx.data_ptr(), gx.stride(0), gx.stride(1),
+                       gx.stride(2), _p(idx), 1 if acc else 0, self.st)
+
+            self.tape.append(bwd)
+        return out
+
+    def pixel_shuffle(self, x, out, mask=None):
+        """nn.PixelShuffle(2) (+ Dropout2d scale): out (N,2h,2w,c/4)."""
+        n, h, w, c4 = x.shape
+        c = c4 // 4
+        L.call("pmfb_pixel_shuffle", C.byref(_view(x.t)), n, h, w, c, _p(mask), out.t.data_ptr(), out.t.stride(0),
+               out.t.stride(1), out.t.stride(2), 1, self.st)
+        if self.record and x.needs_grad:
+            def bwd():
+                g = out.grad_read()
+                gx, acc = x.grad_target()
+                L.call("pmfb_pixel_shuffle_bwd", C.byref(_view(g)), n, h, w, c, _p(mask), gx.data_ptr(), gx.stride(0),
+                       gx.stride(1), gx.stride(2), 1 if acc else 0, 1 if x.round_grad else 0, self.st)
+
+            self.tape.append(bwd)
+        return out
+
+    def upsample2x(self, x, out):
+        n, h, w, c = x.shape
+        L.call("pmfb_upsample2x", C.byref(_view(x.t)), n, h, w, c, out.t.data_ptr(), out.t.stride(0), out.t.stride(1),
+               out.t.stride(2), 1, self.st)
+        if self.record and x.needs_grad:
+            def bwd():
+                g = out.grad_read()
+                gx, acc = x.grad_target()
+                L.call("pmfb_upsample2x_bwd", C.byref(_view(g)), n, h, w, c, gx.data_ptr(), gx.stride(0), gx.stride(1),
+                       gx.stride(2), 1 if acc else 0, self.st)
+
+            self.tape.append(bwd)
+        return out
+
+    def global_avg(self, x):
+        """AdaptiveAvgPool2d(1): (N,h,w,C) -> (N,1,1,C)."""
+        n, h, w, c = x.shape
+        s = self.d64.take(n * c)
+        L.call("pmfb_colsum", C.byref(_view(x.t)), n, h, w, c, 1, s.data_ptr(), self.st)
+        out = self.new(n, 1, 1, c)
+        L.call("pmfb_d2f", s.data_ptr(), out.t.data_ptr(), n * c, 1.0 / (h * w), 0, 1, self.st)
+        if self.record and x.needs_grad:
+            def bwd():
+                g = out.grad_read()  # (N,1,1,C)
+                gx, acc = x.grad_target()
+                scale = torch.full((c,), 1.0 / (h * w), device=self.device, dtype=torch.float32)
+                bv = View()
+                bv.ptr, bv.sn, bv.sy, bv.sx = g.data_ptr(), g.stride(0), 0, 0
+                self.pointwise(bv, gx, alpha1=scale, r1=gx if acc else None, rnd=1 if x.round_grad else 0)
+
+            self.tape.append(bwd)
+        return out
+
+    def broadcast(self, v, out):
+        """(N,1,1,C) -> (N,h,w,C) (F.interpolate of a 1x1 map, pmf_net.py:124-125)."""
+        n, h, w, c = out.shape
+        bv = View()
+        bv.ptr, bv.sn, bv.sy, bv.sx = v.t.data_ptr(), v.t.stride(0), 0, 0
+        self.pointwise(bv, out.t)
+        if self.record and v.needs_grad:
+            def bwd():
+                g = out.grad_read()
+                s = self.d64.take(n * c)
+                L.call("pmfb_colsum", C.byref(_view(g)), n, h, w, c, 1, s.data_ptr(), self.st)
+                gv, acc = v.grad_target()
+                L.call("pmfb_d2f", s.data_ptr(), gv.data_ptr(), n * c, 1.0, 1 if acc else 0, 1 if v.round_grad else 0, self.st)
+
+            self.tape.append(bwd)
+        return out
+
+    def softmax_nchw(self, logits, nclasses):
+        """F.softmax(dim=1) -> dense NCHW probabilities (the module's return value)."""
+        n, h, w, _ = logits.shape
+        out = torch.empty((n, nclasses, h, w), device=self.device, dtype=torch.float32)
+        L.call("pmfb_softmax_nchw", C.byref(_view(logits.t)), n, h, w, nclasses, out.data_ptr(), self.st)
+        return out
+
+    def softmax_backward(self, logits, probs, dprobs):
+        n, h, w, _ = logits.shape
+        if not dprobs.is_contiguous():
+            dprobs = dprobs.contiguous()
+        g, acc = logits.grad_target()
+        assert not acc
+        L.call("pmfb_softmax_nchw_bwd", probs.data_ptr(), dprobs.data_ptr(), n, h, w, probs.shape[1], g.data_ptr(), g.stride(0),
+               g.stride(1), g.stride(2), 1, self.st)
+
+    # ------------------------------------------------------------------------------------------ tape
+    def finish_forward(self):
+        if self.train and self.nbt_list:
+            torch._foreach_add_(self.nbt_list, 1)  # num_batches_tracked bookkeeping (host-side plumbing)
+            self.nbt_list = []
+
+    def run_backward(self):
+        self.st = torch.cuda.current_stream(self.device).cuda_stream
+        self.d64 = _Scratch(torch.float64, 1 << 17, self.device, self.st, zero=True)
+        self.f32.stream = self.st
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+        return self.param_grads

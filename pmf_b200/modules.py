@@ -1,0 +1,320 @@
+"""nn.Module mirrors of the reference's hot-path modules, with the reference's constructor/forward signatures and
+``state_dict`` keys, whose forward/backward run on libpmf_b200.so.
+
+  PMFNet(pcd_channels=5, img_channels=3, nclasses=20, base_channels=32, imagenet_pretrained=True,
+         image_backbone="resnet34").forward(pcd_feature, img_feature) -> (lidar_pred, camera_pred)   pmf_net.py:224-249
+  ResidualBasedFusionBlock(pcd_channels, img_channels).forward(pcd_feature, img_feature) -> Tensor    pmf_net.py:10-36
+
+The child modules (nn.Conv2d / nn.BatchNorm2d / nn.Dropout2d ...) are PARAMETER CONTAINERS created in the
+reference's construction order (so a given torch seed yields the reference's default initialisation, and
+optimisers, DDP, ``replaceBN`` and ``load_state_dict`` see the tree they expect).  Their own ``forward`` is never
+called: the whole network runs as one autograd.Function over pmf_b200.engine.  There is no CPU path — calling a
+module with CPU tensors raises.
+"""
+import torch
+import torch.nn as nn
+
+from . import net as G
+from .engine import Act, Engine, WeightCache
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("pmf_b200 modules run on a B200 (sm_100a) only; got a %s tensor. There is no CPU fallback "
+                               "(use the reference implementation for CPU runs)." % t.device)
+
+
+# ------------------------------------------------------------------------------------------ containers (salsanext.py)
+class ResContextBlock(nn.Module):
+    """Parameters of salsanext.py:9-21."""
+
+    def __init__(self, in_filters, out_filters):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_filters, out_filters, kernel_size=(1, 1), stride=1)
+        self.act1 = nn.LeakyReLU()
+        self.conv2 = nn.Conv2d(out_filters, out_filters, (3, 3), padding=1)
+        self.act2 = nn.LeakyReLU()
+        self.bn1 = nn.BatchNorm2d(out_filters)
+        self.conv3 = nn.Conv2d(out_filters, out_filters, (3, 3), dilation=2, padding=2)
+        self.act3 = nn.LeakyReLU()
+        self.bn2 = nn.BatchNorm2d(out_filters)
+
+
+class ResBlock(nn.Module):
+    """Parameters of salsanext.py:38-67."""
+
+    def __init__(self, in_filters, out_filters, dropout_rate, kernel_size=(3, 3), stride=1, pooling=True, drop_out=True):
+        super().__init__()
+        self.pooling = pooling
+        self.drop_out = drop_out
+        self.conv1 = nn.Conv2d(in_filters, out_filters, kernel_size=(1, 1), stride=stride)
+        self.act1 = nn.LeakyReLU()
+        self.conv2 = nn.Conv2d(in_filters, out_filters, kernel_size=(3, 3), padding=1)
+        self.act2 = nn.LeakyReLU()
+        self.bn1 = nn.BatchNorm2d(out_filters)
+        self.conv3 = nn.Conv2d(out_filters, out_filters, kernel_size=(3, 3), dilation=2, padding=2)
+        self.act3 = nn.LeakyReLU()
+        self.bn2 = nn.BatchNorm2d(out_filters)
+        self.conv4 = nn.Conv2d(out_filters, out_filters, kernel_size=(2, 2), dilation=2, padding=1)
+        self.act4 = nn.LeakyReLU()
+        self.bn3 = nn.BatchNorm2d(out_filters)
+        self.conv5 = nn.Conv2d(out_filters * 3, out_filters, kernel_size=(1, 1))
+        self.act5 = nn.LeakyReLU()
+        self.bn4 = nn.BatchNorm2d(out_filters)
+        self.dropout = nn.Dropout2d(p=dropout_rate)
+        if pooling:
+            self.pool = nn.AvgPool2d(kernel_size=kernel_size, stride=2, padding=1)
+
+
+class UpBlock(nn.Module):
+    """Parameters of salsanext.py:107-134."""
+
+    def __init__(self, in_filters, out_filters, dropout_rate, drop_out=True):
+        super().__init__()
+        self.drop_out = drop_out
+        self.in_filters = in_filters
+        self.out_filters = out_filters
+        self.dropout1 = nn.Dropout2d(p=dropout_rate)
+        self.dropout2 = nn.Dropout2d(p=dropout_rate)
+        self.conv1 = nn.Conv2d(in_filters // 4 + 2 * out_filters, out_filters, (3, 3), padding=1)
+        self.act1 = nn.LeakyReLU()
+        self.bn1 = nn.BatchNorm2d(out_filters)
+        self.conv2 = nn.Conv2d(out_filters, out_filters, (3, 3), dilation=2, padding=2)
+        self.act2 = nn.LeakyReLU()
+        self.bn2 = nn.BatchNorm2d(out_filters)
+        self.conv3 = nn.Conv2d(out_filters, out_filters, (2, 2), dilation=2, padding=1)
+        self.act3 = nn.LeakyReLU()
+        self.bn3 = nn.BatchNorm2d(out_filters)
+        self.conv4 = nn.Conv2d(out_filters * 3, out_filters, kernel_size=(1, 1))
+        self.act4 = nn.LeakyReLU()
+        self.bn4 = nn.BatchNorm2d(out_filters)
+        self.dropout3 = nn.Dropout2d(p=dropout_rate)
+
+
+# ------------------------------------------------------------------------------------------ pmf_net.py
+def _fusion_layers(mod, pcd_channels, img_channels):
+    mod.fuse_conv = nn.Sequential(
+        nn.Conv2d(pcd_channels + img_channels, pcd_channels, kernel_size=3, padding=1, stride=1),
+        nn.LeakyReLU(),
+        nn.BatchNorm2d(pcd_channels))
+    mod.attention = nn.Sequential(
+        nn.Conv2d(pcd_channels, pcd_channels, kernel_size=3, padding=1, stride=1),
+        nn.BatchNorm2d(pcd_channels),
+        nn.ReLU(inplace=True),
+        nn.Conv2d(pcd_channels, pcd_channels, kernel_size=3, padding=1, stride=1),
+        nn.BatchNorm2d(pcd_channels),
+        nn.Sigmoid())
+
+
+class _FusionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, record, pcd, img, *params):
+        E = Engine(G.ModuleParams(mod), pcd.device, mod.training, record, mod._cache, dropout=False)
+        n, cp, h, w = pcd.shape
+        ci = img.shape[1]
+        cat = E.new(n, h, w, cp + ci, needs_grad=True)
+        E.input_nchw(pcd, cp, out=cat.slice(0, cp))
+        E.input_nchw(img, ci, out=cat.slice(cp, cp + ci))
+        y = G.fusion_block(E, cat, cp, "", rnd=False)
+        E.finish_forward()
+        ctx.E, ctx.cat, ctx.y, ctx.cp, ctx.names = E, cat, y, cp, [n_ for n_, _ in mod.named_parameters()]
+        return E.to_nchw(y.t, cp)
+
+    @staticmethod
+    def backward(ctx, dout):
+        E, cat, y, cp = ctx.E, ctx.cat, ctx.y, ctx.cp
+        E.st = torch.cuda.current_stream(dout.device).cuda_stream
+        gy, _ = y.grad_target()
+        E.input_nchw(dout, cp, out=Act(gy, needs_grad=False), rnd=False)
+        grads = E.run_backward()
+        g = cat.grad_read()
+        dp = E.to_nchw(g[..., :cp], cp)
+        di = E.to_nchw(g[..., cp:], g.shape[3] - cp)
+        return (None, None, dp, di) + tuple(grads.get(nm) for nm in ctx.names)
+
+
+class ResidualBasedFusionBlock(nn.Module):
+    """pmf_net.py:10-36: out = f*sigmoid-gate(f) + pcd with f = BN(LeakyReLU(conv3x3(cat(pcd, img))))."""
+
+    def __init__(self, pcd_channels, img_channels):
+        super().__init__()
+        _fusion_layers(self, pcd_channels, img_channels)
+        self._cache = WeightCache()
+
+    def forward(self, pcd_feature, img_feature):
+        _require_cuda(pcd_feature, img_feature)
+        if pcd_feature.shape[1] % 4 or img_feature.shape[1] % 4:
+            raise RuntimeError("pmf_b200 ResidualBasedFusionBlock needs channel counts that are multiples of 4")
+        params = [p for _, p in self.named_parameters()]
+        record = torch.is_grad_enabled() and (pcd_feature.requires_grad or img_feature.requires_grad
+                                              or any(p.requires_grad for p in params))
+        return _FusionFn.apply(self, record, pcd_feature, img_feature, *params)
+
+
+class ResNet(nn.Module):
+    """Parameters of pmf_net.py:41-81 (torchvision blocks, stride-1 7x7 stem)."""
+
+    def __init__(self, in_channels=3, backbone="resnet50", dropout_rate=0.2, pretrained=True):
+        super().__init__()
+        from torchvision.models.resnet import resnet34, resnet50, resnet101, resnet152
+        ctors = {"resnet34": (resnet34, 1), "resnet50": (resnet50, 4), "resnet101": (resnet101, 4), "resnet152": (resnet152, 4)}
+        if backbone not in ctors:
+            raise NotImplementedError("invalid backbone: {}".format(backbone))
+        ctor, self.expansion = ctors[backbone]
+        net = ctor(pretrained)
+        self.feature_channels = [64 * self.expansion, 128 * self.expansion, 256 * self.expansion, 512 * self.expansion]
+        self.backbone_name = backbone
+        self.conv1 = nn.Conv2d(in_channels, 64, kernel_size=7, stride=1, padding=3, bias=False)
+        if in_channels == 3:
+            self.conv1.weight.data = net.conv1.weight.data
+        self.bn1 = net.bn1
+        self.relu = net.relu
+        self.maxpool = net.maxpool
+        self.layer1 = net.layer1
+        self.layer2 = net.layer2
+        self.layer3 = net.layer3
+        self.layer4 = net.layer4
+        self.dropout = nn.Dropout2d(p=dropout_rate)
+
+
+class ASPP(nn.Module):
+    """Parameters of pmf_net.py:103-117."""
+
+    def __init__(self, in_channel=512, depth=256):
+        super().__init__()
+        self.mean = nn.AdaptiveAvgPool2d((1, 1))
+        self.conv = nn.Conv2d(in_channel, depth, 1, 1)
+        self.atrous_block1 = nn.Conv2d(in_channel, depth, 1, 1)
+        self.atrous_block6 = nn.Conv2d(in_channel, depth, 3, 1, padding=6, dilation=6)
+        self.atrous_block12 = nn.Conv2d(in_channel, depth, 3, 1, padding=12, dilation=12)
+        self.atrous_block18 = nn.Conv2d(in_channel, depth, 3, 1, padding=18, dilation=18)
+        self.conv_1x1_output = nn.Conv2d(depth * 5, depth, 1, 1)
+
+
+class SalsaNextFusion(nn.Module):
+    """Parameters of salsanext.py:166-187 + pmf_net.py:141-151, created in the reference's order."""
+
+    def __init__(self, in_channels=8, nclasses=20, base_channels=32, img_feature_channels=()):
+        super().__init__()
+        b = base_channels
+        self.base_channels = b
+        self.dropout_ratio = 0.2
+        self.downCntx = ResContextBlock(in_channels, b)
+        self.downCntx2 = ResContextBlock(b, b)
+        self.downCntx3 = ResContextBlock(b, b)
+        self.resBlock1 = ResBlock(b, 2 * b, self.dropout_ratio, pooling=True, drop_out=False)
+        self.resBlock2 = ResBlock(2 * b, 4 * b, self.dropout_ratio, pooling=True)
+        self.resBlock3 = ResBlock(4 * b, 8 * b, self.dropout_ratio, pooling=True)
+        self.resBlock4 = ResBlock(8 * b, 8 * b, self.dropout_ratio, pooling=True)
+        self.resBlock5 = ResBlock(8 * b, 8 * b, self.dropout_ratio, pooling=False)
+        self.upBlock1 = UpBlock(8 * b, 4 * b, self.dropout_ratio)
+        self.upBlock2 = UpBlock(4 * b, 4 * b, self.dropout_ratio)
+        self.upBlock3 = UpBlock(4 * b, 2 * b, self.dropout_ratio)
+        self.upBlock4 = UpBlock(2 * b, b, self.dropout_ratio, drop_out=False)
+        self.logits = nn.Conv2d(b, nclasses, kernel_size=(1, 1))
+        self.softmax = True
+        self.fusionblock_1 = _FusionContainer(2 * b, img_feature_channels[0])
+        self.fusionblock_2 = _FusionContainer(4 * b, img_feature_channels[1])
+        self.fusionblock_3 = _FusionContainer(8 * b, img_feature_channels[2])
+        self.fusionblock_4 = _FusionContainer(8 * b, img_feature_channels[3])
+        self.aspp = ASPP(8 * b, 8 * b)
+
+
+class _FusionContainer(nn.Module):
+    def __init__(self, pcd_channels, img_channels):
+        super().__init__()
+        _fusion_layers(self, pcd_channels, img_channels)
+
+
+class RGBDecoder(nn.Module):
+    """Parameters of pmf_net.py:183-212."""
+
+    def __init__(self, in_channels=(), nclasses=4, base_channels=64):
+        super().__init__()
+
+        def stage(cin, k, pad):
+            return nn.Sequential(nn.Conv2d(cin, base_channels, k, padding=pad), nn.LeakyReLU(), nn.BatchNorm2d(base_channels),
+                                 nn.Upsample(scale_factor=2, mode="bilinear"))
+
+        self.up_4a = stage(in_channels[3], 3, 1)
+        self.up_3a = stage(in_channels[2] + base_channels, 3, 1)
+        self.up_2a = stage(in_channels[1] + base_channels, 3, 1)
+        self.up_1a = stage(in_channels[0] + base_channels, 1, 0)
+        self.conv = nn.Conv2d(base_channels, nclasses, kernel_size=3, padding=1)
+
+
+class _PMFFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, record, pcd, img, *params):
+        E = Engine(G.ModuleParams(mod), pcd.device, mod.training, record, mod._cache, dropout=mod._dropout_masks())
+        lidar, camera, ll, cl = G.pmf_forward(E, pcd, img, mod.image_backbone, mod.nclasses)
+        if record:
+            ctx.E, ctx.ll, ctx.cl = E, ll, cl
+            ctx.names = [n for n, _ in mod.named_parameters()]
+            ctx.save_for_backward(lidar, camera)
+        else:
+            ctx.E = None
+        return lidar, camera
+
+    @staticmethod
+    def backward(ctx, d_lidar, d_camera):
+        E = ctx.E
+        if E is None:
+            raise RuntimeError("pmf_b200: backward through a forward that was run without gradient recording")
+        lidar, camera = ctx.saved_tensors
+        E.st = torch.cuda.current_stream(lidar.device).cuda_stream
+        E.softmax_backward(ctx.ll, lidar, d_lidar)
+        E.softmax_backward(ctx.cl, camera, d_camera)
+        grads = E.run_backward()
+        ctx.E = None
+        return (None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
+
+
+class PMFNet(nn.Module):
+    """pmf_net.py:224-249.  forward returns the two softmax probability maps (B, nclasses, H, W)."""
+
+    def __init__(self, pcd_channels=5, img_channels=3, nclasses=20, base_channels=32, imagenet_pretrained=True,
+                 image_backbone="resnet34"):
+        super().__init__()
+        self.camera_stream_encoder = ResNet(in_channels=img_channels, pretrained=imagenet_pretrained, backbone=image_backbone)
+        self.camera_stream_decoder = RGBDecoder(self.camera_stream_encoder.feature_channels, nclasses=nclasses,
+                                                base_channels=self.camera_stream_encoder.expansion * 16)
+        self.lidar_stream = SalsaNextFusion(in_channels=pcd_channels, nclasses=nclasses, base_channels=base_channels,
+                                            img_feature_channels=self.camera_stream_encoder.feature_channels)
+        self.nclasses = nclasses
+        self.image_backbone = image_backbone
+        self._cache = WeightCache()
+        self._dropout_override = None  # tests: False (off) or {site: (N,C) mask}
+
+    def _dropout_masks(self):
+        if self._dropout_override is not None:
+            return self._dropout_override
+        if not self.training:
+            return False
+        # honour per-module .eval() on the Dropout2d children (sites whose module is in eval mode are skipped)
+        return _DropoutSites(self)
+
+    def forward(self, pcd_feature, img_feature):
+        _require_cuda(pcd_feature, img_feature)
+        params = [p for _, p in self.named_parameters()]
+        record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _PMFFn.apply(self, record, pcd_feature, img_feature, *params)
+
+
+class _DropoutSites(dict):
+    """Lazily answers Engine.mask_for(site): draws a fresh Dropout2d scale when the site's module is training."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.mods = dict(model.named_modules())
+
+    def draw(self, site, n, c, device):
+        name = site
+        if ".dropout.layer" in site:  # camera_stream_encoder.dropout.layer3 -> camera_stream_encoder.dropout
+            name = site[:site.index(".dropout.layer")] + ".dropout"
+        mod = self.mods.get(name)
+        if mod is None or not mod.training or mod.p <= 0.0:
+            return None
+        keep = 1.0 - float(mod.p)
+        return torch.empty((n, c), device=device, dtype=torch.float32).bernoulli_(keep).div_(keep)

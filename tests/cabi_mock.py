@@ -1,0 +1,442 @@
+"""TEST INFRASTRUCTURE: a numpy model of the C-ABI in include/pmfb.h, operating on raw host pointers.
+
+It exists so that the HOST logic above the boundary (pmf_b200.engine / pmf_b200.net: graph wiring, tap generation,
+stride-2 parity decomposition, gradient-slice bookkeeping, BatchNorm backward plumbing) can be checked against the
+oracle on the CPU-only build box, where the CUDA library cannot execute.  It is injected by
+``install(monkeypatch)`` into ``pmf_b200._lib.call`` for the duration of one test; nothing in the product imports
+it, and the product modules refuse CPU tensors.  The ``-m gpu`` tests never use it.
+"""
+import ctypes as C
+
+import numpy as np
+
+from pmf_b200 import _lib as L
+
+F32 = np.float32
+
+
+def _arr(ptr, shape, strides_elems, dtype=np.float32):
+    item = np.dtype(dtype).itemsize
+    if isinstance(ptr, C.c_void_p):
+        ptr = ptr.value
+    # span of the strided view in elements
+    span = 1 + sum((s - 1) * abs(st) for s, st in zip(shape, strides_elems)) if all(s > 0 for s in shape) else 1
+    ctype = {np.float32: C.c_float, np.float64: C.c_double, np.int32: C.c_int32, np.int64: C.c_int64, np.uint8: C.c_uint8}[dtype]
+    base = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(span,))
+    return np.lib.stride_tricks.as_strided(base, shape=shape, strides=[s * item for s in strides_elems])
+
+
+def _vec(ptr, n, dtype=np.float32):
+    return None if not ptr else _arr(ptr, (n,), (1,), dtype)
+
+
+def _view(v, n, h, w, c):
+    if v is None or not v.ptr:
+        return None
+    return _arr(v.ptr, (n, h, w, c), (v.sn, v.sy, v.sx, 1))
+
+
+def _deref(p):
+    if p is None:
+        return None
+    try:
+        return p._obj  # byref()
+    except AttributeError:
+        return p.contents if p else None
+
+
+EXACT = False  # True: model the library with exact fp32 operands (no tf32 rounding) -> sharp wiring checks
+
+
+def rtf32(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if EXACT:
+        return x
+    b = x.view(np.int32)
+    return ((b + 0x1000) & ~np.int32(0x1FFF)).view(np.float32)
+
+
+def _act(a, v):
+    if a == L.ACT_RELU:
+        return np.maximum(v, 0)
+    if a == L.ACT_LEAKY:
+        return np.where(v > 0, v, F32(0.01) * v)
+    if a == L.ACT_SIGMOID:
+        return (1.0 / (1.0 + np.exp(-v.astype(np.float64)))).astype(np.float32)
+    return v
+
+
+def _act_grad(a, z):
+    if a == L.ACT_RELU:
+        return (z > 0).astype(np.float32)
+    if a == L.ACT_LEAKY:
+        return np.where(z > 0, F32(1), F32(0.01))
+    if a == L.ACT_SIGMOID:
+        return z * (1 - z)
+    return np.ones_like(z)
+
+
+def _epilogue(e, v, n, h, w, c, c0=0):
+    """v: (n,h,w,c) values for channels c0..c0+c."""
+    v = v.astype(np.float32)
+    if e.alpha1:
+        v = v * _vec(e.alpha1, c0 + c)[c0:]
+    if e.beta1:
+        v = v + _vec(e.beta1, c0 + c)[c0:]
+    r1 = _view(e.r1, n, h, w, c0 + c)
+    if r1 is not None:
+        v = v + r1[..., c0:]
+    v = _act(e.act, v)
+    if e.alpha2:
+        v = v * _vec(e.alpha2, c0 + c)[c0:]
+    if e.beta2:
+        v = v + _vec(e.beta2, c0 + c)[c0:]
+    mul = _view(e.mul, n, h, w, c0 + c)
+    if mul is not None:
+        v = v * mul[..., c0:]
+    r2 = _view(e.r2, n, h, w, c0 + c)
+    if r2 is not None:
+        v = v + r2[..., c0:]
+    if e.round_out:
+        v = rtf32(v)
+    return v.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------- functions
+def pmfb_memset_zero(ptr, nbytes, stream):
+    C.memset(ptr, 0, nbytes)
+
+
+def pmfb_pack_input(src, s_n, s_c, s_h, s_w, n, c, h, w, n_shift, dst, c_dst, dps, rnd, stream):
+    x = _arr(src, (n, c, h, w), (s_n, s_c, s_h, s_w))
+    out = _arr(dst, (n, h, w, c_dst), (h * w * dps, w * dps, dps, 1))
+    res = np.zeros((n, h, w, c_dst), np.float32)
+    half = n_shift // 2
+    for s in range(n_shift):
+        sh = s - half
+        for ch in range(c):
+            plane = np.zeros((n, h, w), np.float32)
+            if sh >= 0:
+                plane[:, :, :w - sh] = x[:, ch, :, sh:]
+            else:
+                plane[:, :, -sh:] = x[:, ch, :, :w + sh]
+            res[..., s * c + ch] = plane
+    out[...] = rtf32(res) if rnd else res
+
+
+def pmfb_nhwc_to_nchw(src, n, h, w, c, dst, stream):
+    v = _view(_deref(src), n, h, w, c)
+    _arr(dst, (n, c, h, w), (c * h * w, h * w, w, 1))[...] = np.transpose(v, (0, 3, 1, 2))
+
+
+def pmfb_pack_weight(wp, c_out, c_in, kh, kw, stem, c_out_p, c_in_p, fwd, dgrad, stream):
+    w = _arr(wp, (c_out, c_in, kh, kw), (c_in * kh * kw, kh * kw, kw, 1))
+    taps = kh if stem else kh * kw
+    pk = np.zeros((taps, c_out_p, c_in_p), np.float32)
+    if stem:
+        for ki in range(kh):
+            for kj in range(kw):
+                pk[ki, :c_out, kj * c_in:(kj + 1) * c_in] = w[:, :, ki, kj]
+    else:
+        pk[:, :c_out, :c_in] = np.transpose(w.reshape(c_out, c_in, taps), (2, 0, 1))
+    pk = rtf32(pk)
+    if fwd:
+        _arr(fwd, pk.shape, (c_out_p * c_in_p, c_in_p, 1))[...] = pk
+    if dgrad:
+        _arr(dgrad, (taps, c_in_p, c_out_p), (c_in_p * c_out_p, c_out_p, 1))[...] = np.transpose(pk, (0, 2, 1))
+
+
+def pmfb_unpack_wgrad(packed, c_out, c_in, kh, kw, stem, c_out_p, c_in_p, grad, accumulate, stream):
+    taps = kh if stem else kh * kw
+    pk = _arr(packed, (taps, c_in_p, c_out_p), (c_in_p * c_out_p, c_out_p, 1))
+    g = np.zeros((c_out, c_in, kh, kw), np.float32)
+    if stem:
+        for ki in range(kh):
+            for kj in range(kw):
+                g[:, :, ki, kj] = pk[ki, kj * c_in:(kj + 1) * c_in, :c_out].T
+    else:
+        g = np.transpose(pk[:, :c_in, :c_out], (2, 1, 0)).reshape(c_out, c_in, kh, kw)
+    out = _arr(grad, (c_out, c_in, kh, kw), (c_in * kh * kw, kh * kw, kw, 1))
+    out[...] = out + g if accumulate else g
+
+
+def pmfb_pointwise(inp, out, o_sn, o_sy, o_sx, n, h, w, c, epi, stream):
+    v = _view(_deref(inp), n, h, w, c)
+    if v is None:
+        v = np.zeros((n, h, w, c), np.float32)
+    res = _epilogue(_deref(epi), np.array(v), n, h, w, c)
+    _arr(out, (n, h, w, c), (o_sn, o_sy, o_sx, 1))[...] = res
+
+
+def pmfb_bn_stats(x, n, h, w, c, sums, stream):
+    v = _view(_deref(x), n, h, w, c).astype(np.float64)
+    s = _vec(sums, 2 * c, np.float64)
+    s[:c] += v.sum((0, 1, 2))
+    s[c:] += (v * v).sum((0, 1, 2))
+
+
+def pmfb_colsum(x, n, h, w, c, per_image, out, stream):
+    v = _view(_deref(x), n, h, w, c).astype(np.float64)
+    if per_image:
+        _arr(out, (n, c), (c, 1), np.float64)[...] += v.sum((1, 2))
+    else:
+        _vec(out, c, np.float64)[...] += v.sum((0, 1, 2))
+
+
+def pmfb_d2f(src, dst, n, scale, accumulate, rnd, stream):
+    v = (_vec(src, n, np.float64) * float(scale)).astype(np.float32)
+    d = _vec(dst, n)
+    if accumulate:
+        v = v + d
+    d[...] = rtf32(v) if rnd else v
+
+
+def pmfb_bn_finalize(sums, count, c, gamma, beta, rm, rv, momentum, eps, alpha, beta_out, mean_out, invstd_out, stream):
+    if sums:
+        s = _vec(sums, 2 * c, np.float64)
+        m = s[:c] / count
+        v = np.maximum(s[c:] / count - m * m, 0)
+        mean, var = m.astype(np.float32), v.astype(np.float32)
+        if rm:
+            r = _vec(rm, c)
+            r[...] = F32(1 - momentum) * r + F32(momentum) * mean
+        if rv:
+            r = _vec(rv, c)
+            unb = (v * count / (count - 1)).astype(np.float32) if count > 1 else var
+            r[...] = F32(1 - momentum) * r + F32(momentum) * unb
+    else:
+        mean, var = np.array(_vec(rm, c)), np.array(_vec(rv, c))
+    invstd = (1.0 / np.sqrt(var + F32(eps))).astype(np.float32)
+    g = _vec(gamma, c) if gamma else np.ones(c, np.float32)
+    b = _vec(beta, c) if beta else np.zeros(c, np.float32)
+    a = g * invstd
+    if alpha:
+        _vec(alpha, c)[...] = a
+    if beta_out:
+        _vec(beta_out, c)[...] = b - mean * a
+    if mean_out:
+        _vec(mean_out, c)[...] = mean
+    if invstd_out:
+        _vec(invstd_out, c)[...] = invstd
+
+
+def _grad_in(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c):
+    g = np.array(_view(_deref(dy), n, h, w, c))
+    m = _view(_deref(mul), n, h, w, c)
+    if m is not None:
+        g = g * m
+    xv = _view(_deref(x), n, h, w, c)
+    xv = np.zeros_like(g) if xv is None else np.array(xv)
+    if act_z:
+        zz = _view(_deref(z), n, h, w, c)
+        if zz is None:
+            zz = _act(act_z, _vec(alpha, c) * xv + _vec(beta, c))
+        g = g * _act_grad(act_z, zz)
+    xhat = (xv - _vec(mean, c)) * _vec(invstd, c) if mean else np.zeros_like(g)
+    return g.astype(np.float32), xhat.astype(np.float32), xv
+
+
+def pmfb_bn_bwd_reduce(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c, red, stream):
+    g, xhat, _ = _grad_in(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c)
+    r = _vec(red, 2 * c, np.float64)
+    r[:c] += g.astype(np.float64).sum((0, 1, 2))
+    r[c:] += (g.astype(np.float64) * xhat).sum((0, 1, 2))
+
+
+def pmfb_bn_bwd_apply(dy, mul, z, act_z, x, mean, invstd, alpha, beta, gamma, red, leaky_x, n, h, w, c, dx, d_sn, d_sy,
+                      d_sx, rnd, dgamma, dbeta, colsum, g_out, g_sn, g_sy, g_sx, g_acc, stream):
+    g, xhat, xv = _grad_in(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c)
+    if g_out:
+        go = _arr(g_out, (n, h, w, c), (g_sn, g_sy, g_sx, 1))
+        go[...] = go + g if g_acc else g
+    d = g
+    if mean:
+        r = _vec(red, 2 * c, np.float64)
+        cnt = n * h * w
+        m1, m2 = (r[:c] / cnt).astype(np.float32), (r[c:] / cnt).astype(np.float32)
+        d = _vec(gamma, c) * _vec(invstd, c) * (g - m1 - xhat * m2)
+        if dgamma:
+            _vec(dgamma, c)[...] = r[c:].astype(np.float32)
+        if dbeta:
+            _vec(dbeta, c)[...] = r[:c].astype(np.float32)
+    if leaky_x:
+        d = d * np.where(xv > 0, F32(1), F32(0.01))
+    d = d.astype(np.float32)
+    if rnd:
+        d = rtf32(d)
+    if dx:
+        _arr(dx, (n, h, w, c), (d_sn, d_sy, d_sx, 1))[...] = d
+    if colsum:
+        _vec(colsum, c, np.float64)[...] += d.astype(np.float64).sum((0, 1, 2))
+
+
+def pmfb_pool3s2(kind, x, n, h, w, c, chan_scale, out, o_sn, o_sy, o_sx, idx, rnd, stream):
+    v = np.array(_view(_deref(x), n, h, w, c))
+    ho, wo = h // 2, w // 2
+    pad = np.full((n, h + 2, w + 2, c), 0.0 if kind == 0 else -np.inf, np.float32)
+    pad[:, 1:-1, 1:-1] = v
+    wins = np.stack([pad[:, i:i + 2 * ho:2, j:j + 2 * wo:2] for i in range(3) for j in range(3)], 0)
+    if kind == 0:
+        res = wins.sum(0, dtype=np.float32) / F32(9)
+    else:
+        am = wins.argmax(0)
+        res = wins.max(0)
+        if idx:
+            _arr(idx, (n, ho, wo, c), (ho * wo * c, wo * c, c, 1), np.uint8)[...] = am.astype(np.uint8)
+    if chan_scale:
+        res = res * _arr(chan_scale, (n, 1, 1, c), (c, 0, 0, 1))
+    _arr(out, (n, ho, wo, c), (o_sn, o_sy, o_sx, 1))[...] = rtf32(res) if rnd else res
+
+
+def pmfb_pool3s2_bwd(kind, dy, n, h, w, c, chan_scale, dx, d_sn, d_sy, d_sx, idx, accumulate, stream):
+    ho, wo = h // 2, w // 2
+    g = np.array(_view(_deref(dy), n, ho, wo, c))
+    acc = np.zeros((n, h + 2, w + 2, c), np.float32)
+    am = _arr(idx, (n, ho, wo, c), (ho * wo * c, wo * c, c, 1), np.uint8) if (kind == 1) else None
+    for t in range(9):
+        i, j = t // 3, t % 3
+        contrib = g / F32(9) if kind == 0 else np.where(am == t, g, F32(0))
+        acc[:, i:i + 2 * ho:2, j:j + 2 * wo:2] += contrib
+    res = acc[:, 1:-1, 1:-1]
+    if chan_scale:
+        res = res * _arr(chan_scale, (n, 1, 1, c), (c, 0, 0, 1))
+    o = _arr(dx, (n, h, w, c), (d_sn, d_sy, d_sx, 1))
+    o[...] = o + res if accumulate else res
+
+
+def pmfb_pixel_shuffle(x, n, h, w, c, chan_scale, out, o_sn, o_sy, o_sx, rnd, stream):
+    v = np.array(_view(_deref(x), n, h, w, 4 * c)).reshape(n, h, w, c, 2, 2)
+    res = np.transpose(v, (0, 1, 4, 2, 5, 3)).reshape(n, 2 * h, 2 * w, c)
+    if chan_scale:
+        res = res * _arr(chan_scale, (n, 1, 1, c), (c, 0, 0, 1))
+    _arr(out, (n, 2 * h, 2 * w, c), (o_sn, o_sy, o_sx, 1))[...] = rtf32(res) if rnd else res
+
+
+def pmfb_pixel_shuffle_bwd(dy, n, h, w, c, chan_scale, dx, d_sn, d_sy, d_sx, accumulate, rnd, stream):
+    g = np.array(_view(_deref(dy), n, 2 * h, 2 * w, c))
+    if chan_scale:
+        g = g * _arr(chan_scale, (n, 1, 1, c), (c, 0, 0, 1))
+    res = np.transpose(g.reshape(n, h, 2, w, 2, c), (0, 1, 3, 5, 2, 4)).reshape(n, h, w, 4 * c)
+    o = _arr(dx, (n, h, w, 4 * c), (d_sn, d_sy, d_sx, 1))
+    res = o + res if accumulate else res
+    o[...] = rtf32(res) if rnd else res
+
+
+def _up_matrix(size):
+    m = np.zeros((2 * size, size), np.float32)
+    for o in range(2 * size):
+        s = max(0.5 * (o + 0.5) - 0.5, 0.0)
+        i0 = int(s)
+        i1 = i0 + (1 if i0 < size - 1 else 0)
+        l1 = s - i0
+        m[o, i0] += 1 - l1
+        m[o, i1] += l1
+    return m
+
+
+def pmfb_upsample2x(x, n, h, w, c, out, o_sn, o_sy, o_sx, rnd, stream):
+    v = np.array(_view(_deref(x), n, h, w, c))
+    res = np.einsum("ah,nhwc->nawc", _up_matrix(h), v)
+    res = np.einsum("bw,nawc->nabc", _up_matrix(w), res).astype(np.float32)
+    _arr(out, (n, 2 * h, 2 * w, c), (o_sn, o_sy, o_sx, 1))[...] = rtf32(res) if rnd else res
+
+
+def pmfb_upsample2x_bwd(dy, n, h, w, c, dx, d_sn, d_sy, d_sx, accumulate, stream):
+    g = np.array(_view(_deref(dy), n, 2 * h, 2 * w, c))
+    res = np.einsum("ah,nabc->nhbc", _up_matrix(h), g)
+    res = np.einsum("bw,nhbc->nhwc", _up_matrix(w), res).astype(np.float32)
+    o = _arr(dx, (n, h, w, c), (d_sn, d_sy, d_sx, 1))
+    o[...] = o + res if accumulate else res
+
+
+def pmfb_softmax_nchw(logits, n, h, w, c, out, stream):
+    v = np.array(_view(_deref(logits), n, h, w, c))
+    e = np.exp(v - v.max(-1, keepdims=True))
+    p = e / e.sum(-1, keepdims=True)
+    _arr(out, (n, c, h, w), (c * h * w, h * w, w, 1))[...] = np.transpose(p, (0, 3, 1, 2))
+
+
+def pmfb_softmax_nchw_bwd(p, dp, n, h, w, c, dz, d_sn, d_sy, d_sx, rnd, stream):
+    pv = np.transpose(_arr(p, (n, c, h, w), (c * h * w, h * w, w, 1)), (0, 2, 3, 1))
+    gv = np.transpose(_arr(dp, (n, c, h, w), (c * h * w, h * w, w, 1)), (0, 2, 3, 1))
+    res = pv * (gv - (pv * gv).sum(-1, keepdims=True))
+    cp = (c + 3) // 4 * 4
+    o = _arr(dz, (n, h, w, cp), (d_sn, d_sy, d_sx, 1))
+    o[..., :c] = rtf32(res) if rnd else res
+    o[..., c:] = 0
+
+
+def _tma_gather(src, c_lo, c_n, x0_of, tile):
+    """Zero-filled read of channels [c_lo, c_lo+c_n) for all (n, y, x) of the logical output grid at tap offset."""
+    raise NotImplementedError
+
+
+def _src5(s):
+    dims = [int(d) for d in s.dims]
+    strides = [1] + [int(b) // 4 for b in s.strides]
+    # array indexed [n, h, p, w, c]
+    return _arr(s.ptr, (dims[4], dims[3], dims[2], dims[1], dims[0]), (strides[4], strides[3], strides[2], strides[1], 1))
+
+
+def _tap_read(X, dc, cn, dw, dp, dh, out_h, out_w):
+    """X[n, y+dh, dp, x+dw, dc:dc+cn] with zero fill outside every dimension -> (n, out_h, out_w, cn)."""
+    n, H, P, W, Cc = X.shape
+    out = np.zeros((n, out_h, out_w, cn), np.float32)
+    if dp < 0 or dp >= P:
+        return out
+    y0, y1 = max(0, -dh), min(out_h, H - dh)
+    x0, x1 = max(0, -dw), min(out_w, W - dw)
+    c1 = min(Cc, dc + cn)
+    if y1 > y0 and x1 > x0 and c1 > dc:
+        out[:, y0:y1, x0:x1, :c1 - dc] = X[:, y0 + dh:y1 + dh, dp, x0 + dw:x1 + dw, dc:c1]
+    return out
+
+
+def pmfb_conv_fwd(dp_, stream):
+    d = _deref(dp_)
+    X = _src5(d.x)
+    n_slabs = d.n_taps
+    if d.use_tap_wi:
+        n_slabs = max(n_slabs, max(d.tap_wi[i] for i in range(d.n_taps)) + 1)
+    Wp = _arr(d.w, (n_slabs, d.c_out, d.c_in), (d.c_out * d.c_in, d.c_in, 1))
+    acc = np.zeros((d.n_batch, d.out_h, d.out_w, d.c_out), np.float32)
+    for t in range(d.n_taps):
+        wi = d.tap_wi[t] if d.use_tap_wi else t
+        a = _tap_read(X, d.tap_dc[t], d.c_in, d.tap_dw[t], d.tap_dp[t], d.tap_dh[t], d.out_h, d.out_w)
+        acc += (a.reshape(-1, d.c_in) @ Wp[wi].T).reshape(acc.shape)
+    res = _epilogue(d.epi, acc, d.n_batch, d.out_h, d.out_w, d.c_out)
+    _arr(d.out, acc.shape, (d.o_sn, d.o_sy, d.o_sx, 1))[...] = res
+
+
+def pmfb_conv_wgrad(dp_, stream):
+    d = _deref(dp_)
+    X = _src5(d.x)
+    DY = _src5(d.dy)
+    dy = _tap_read(DY, 0, d.c_out, 0, 0, 0, d.out_h, d.out_w).reshape(-1, d.c_out)
+    dw = _arr(d.dw, (d.n_taps, d.c_in, d.c_out), (d.c_in * d.c_out, d.c_out, 1))
+    for t in range(d.n_taps):
+        a = _tap_read(X, d.tap_dc[t], d.c_in, d.tap_dw[t], d.tap_dp[t], d.tap_dh[t], d.out_h, d.out_w).reshape(-1, d.c_in)
+        dw[t] += a.T @ dy
+
+
+_IMPL = {k: v for k, v in globals().items() if k.startswith("pmfb_")}
+
+
+class _FakeStream:
+    cuda_stream = 0
+
+
+def install(monkeypatch, exact=False):
+    """Route pmf_b200._lib.call to the numpy model and let the Engine run on CPU tensors (tests only)."""
+    import sys
+    import torch
+
+    monkeypatch.setattr(sys.modules[__name__], "EXACT", bool(exact))
+
+    def call(name, *args):
+        L.launches += 1
+        _IMPL[name](*args)
+
+    monkeypatch.setattr(L, "call", call)
+    monkeypatch.setattr(L, "require_device", lambda: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _FakeStream())
