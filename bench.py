@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): frames/sec of one PMF-ResNet34 training step (forward + loss + backward +
+optimizer step) on the SemanticKITTI-shaped synthetic workload — batch 8 per GPU on the 480x640 camera grid
+(a frame = one 64x2048 = 131 072-point sweep perspective-projected onto a 480x640 RGB image).
+
+    python bench.py --gpus 1 --steps K --warmup W                      our arm (libpmf_b200.so through pmf_b200.PMFNet)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   frame-parallel DDP, weak scaling
+    python bench.py --impl reference ...                                the reference's CPU PyTorch path (oracle port)
+
+Prints ONE JSON line on rank 0.  `value` = frames/s with inputs resident in HBM; `e2e` = the same step driven from
+pinned HOST buffers through the public module call (H2D of the (B,8,H,W) frame tensor + labels and D2H of the loss
+inside the timed region).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max
+over ranks.  The per-step working set (tens of GB of activations) is far larger than the 126 MB L2, so no explicit
+L2 flush is needed between iterations (stated in config.l2).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FWD_KFLOP_PER_PX = 1806.6   # PMF-ResNet34 forward, 2*MAC, convs only
+STEP_KFLOP_PER_PX = 5400.7  # forward + dgrad + wgrad (minus the two input dgrads)
+METRIC = "frames/sec PMF-ResNet34 fwd+bwd (480x640 camera grid, batch 8/GPU)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--cpu-sample-frames", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-timing", type=int, default=1, help="extra instrumented step for the roofline object")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ shared pieces
+def make_frames(B, H, W, seed):
+    """(B,8,H,W) normalised frame tensor + (B,H,W) labels, as tasks/pmf/trainer.py:291-299 hands them to the model."""
+    from tests import synth
+    feat, _mask, label = synth.frame_tensor(B, H, W, seed=seed, density=0.1)
+    return feat, label
+
+
+def nll_loss(lidar_pred, camera_pred, label):
+    """A cheap stand-in for the trainer's loss block (trainer.py:305-332) that drives both heads: mean negative
+    log-probability of the labelled class.  Identical in both arms."""
+    t = label.unsqueeze(1)
+    return -(torch.log(lidar_pred.gather(1, t).clamp_min(1e-8)).mean() + torch.log(camera_pred.gather(1, t).clamp_min(1e-8)).mean())
+
+
+def make_optimizers(lidar_params, camera_params):
+    """tasks/pmf/trainer.py:80-98: AdamW(lr 1e-3) on the LiDAR stream, nesterov SGD on the camera encoder+decoder."""
+    return (torch.optim.AdamW(lidar_params, lr=1e-3), torch.optim.SGD(camera_params, lr=1e-3, momentum=0.9, nesterov=True,
+                                                                        weight_decay=1e-5))
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1354.7), d.get("hbm_gbs", 6546.2), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_reference_step_rate(B, H, W, steps, warmup, threads=None):
+    """The reference's CPU PyTorch path for the same step (oracle port of PMFNet: oracle/pmf_oracle.py, fp32,
+    batch-stat BN, dropout inactive) on the host cores.  Returns frames/s."""
+    from oracle import pmf_oracle as po
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(1)
+    shapes = po.pmf_param_shapes(20, 32, "resnet34")
+    sd = po.synth_state_dict(shapes, seed=1)
+    params = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+              for k, v in sd.items()}
+    lidar = [v for k, v in params.items() if k.startswith("lidar_stream") and v.requires_grad]
+    camera = [v for k, v in params.items() if not k.startswith("lidar_stream") and v.requires_grad]
+    opt_a, opt_b = make_optimizers(lidar, camera)
+    feat, label = make_frames(B, H, W, seed=1)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        lid, cam, ctx = po.pmf_forward(params, feat[:, 0:5], feat[:, 5:8], "resnet34", train=True, return_ctx=True)
+        loss = nll_loss(lid, cam, label)
+        opt_a.zero_grad(set_to_none=True)
+        opt_b.zero_grad(set_to_none=True)
+        loss.backward()
+        opt_a.step()
+        opt_b.step()
+        for k, v in ctx.new_stats.items():
+            params[k] = v
+        float(loss)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return B / sec, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    B = max(1, args.cpu_sample_frames)
+    fps, sec = cpu_reference_step_rate(B, args.height, args.width, args.steps, max(args.warmup, 1), threads=cores)
+    sample = "%d frame(s) per step at %dx%d, fwd+loss+bwd+optimizer step, %d warm-up + %d timed steps" % (
+        B, args.height, args.width, max(args.warmup, 1), args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "PMF-ResNet34 SemanticKITTI-shaped synthetic, %dx%d camera grid, CPU sample of %d frame(s)/step"
+                       % (args.height, args.width, B), "frames_per_step": B, "height": args.height, "width": args.width},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    import pmf_b200
+    from pmf_b200 import _lib as L
+    from pmf_b200 import dist as pdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, H, W = args.batch, args.height, args.width
+
+    torch.manual_seed(1)
+    model = pmf_b200.PMFNet(5, 3, 20, 32, False, "resnet34").to(dev)
+    model.train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])  # tasks/pmf/trainer.py:38-39
+    opt_a, opt_b = make_optimizers(list(model.lidar_stream.parameters()),
+                                   list(model.camera_stream_encoder.parameters()) + list(model.camera_stream_decoder.parameters()))
+    # frame-parallel sharding: every rank owns its own B frames (weak scaling), no data-path collective
+    feat, label = make_frames(B, H, W, seed=pdist.shard_seed(1, rank))
+    h_feat, h_label = feat.pin_memory(), label.pin_memory()
+    d_feat, d_label = h_feat.to(dev, non_blocking=True), h_label.to(dev, non_blocking=True)
+    h_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(x, y):
+        lid, cam = net(x[:, 0:5], x[:, 5:8])  # channel-slice views like trainer.py:296-297
+        loss = nll_loss(lid, cam, y)
+        opt_a.zero_grad(set_to_none=True)
+        opt_b.zero_grad(set_to_none=True)
+        loss.backward()
+        opt_a.step()
+        opt_b.step()
+        return loss
+
+    def step_e2e():
+        x = h_feat.to(dev, non_blocking=True)
+        y = h_label.to(dev, non_blocking=True)
+        loss = step(x, y)
+        h_loss.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the user reads the loss every iteration (trainer.py:384-407)
+        return float(h_loss)
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(t)
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step(d_feat, d_label)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = L.launches
+    ms = timed(lambda: step(d_feat, d_label), args.steps)
+    launches = L.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    frames = B * world * args.steps
+    value = frames / (ms * 1e-3)
+    e2e = frames / (ms_e2e * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: the tcgen05 implicit-GEMM conv (forward + dgrad launches), timed live with
+    # CUDA events around every launch of one extra step on the launching stream.
+    peak_tf, peak_bw, peak_src = peaks()
+    roof = None
+    if args.kernel_timing:
+        roof = kernel_roofline(lambda: step(d_feat, d_label), dev, ms / args.steps, peak_tf, peak_src)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        fps, sec = cpu_reference_step_rate(args.cpu_sample_frames, H, W, steps=2, warmup=1, threads=cores)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "%d frame(s)/step at %dx%d (oracle port of the reference's PMFNet, fp32), fwd+loss+bwd+optimizer step, "
+                         "1 warm-up + 2 timed steps" % (args.cpu_sample_frames, H, W)}
+    px = H * W
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+            "data": "synthetic",
+            "config": {"workload": "PMF-ResNet34 SemanticKITTI-shaped synthetic, batch %d/GPU, %dx%d camera grid, "
+                                   "fwd+loss+bwd+AdamW/SGD step, train-mode BN + Dropout2d" % (B, H, W),
+                       "frames_per_gpu": B, "height": H, "width": W, "parallelism": "ddp%d (frame-parallel)" % world,
+                       "l2": "no explicit flush: per-step working set (>20 GB of activations) >> 126 MB L2",
+                       "step_gflop_per_frame": STEP_KFLOP_PER_PX * px / 1e6, "precision": "kind::tf32 operands, fp32 accumulate/storage"},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": h_feat.numel() * 4 + h_label.numel() * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "step_tflops": STEP_KFLOP_PER_PX * 1e3 * px * B / (ms / args.steps * 1e-3) / 1e12,
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
+    """Time every pmfb_conv_fwd launch (forward convs and dgrads) of one step with CUDA events on the launching
+    stream; algorithmic FLOPs per launch = 2 * pixels * c_out * c_in * taps."""
+    from pmf_b200 import _lib as L
+    import ctypes as C
+    recs = []
+    orig = L.call
+
+    def call(name, *a):
+        if name not in ("pmfb_conv_fwd", "pmfb_conv_wgrad"):
+            return orig(name, *a)
+        d = a[0]._obj
+        flops = 2.0 * d.n_batch * d.out_h * d.out_w * d.c_out * d.c_in * d.n_taps
+        if d.n_taps == 7 and d.c_in == 32:
+            flops *= 21.0 / 32.0  # the 7x7x3 stem runs as 7 taps over 21 real (+11 zero) unrolled channels
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(name, *a)
+        e1.record()
+        recs.append((name, flops, e0, e1))
+
+    L.call = call
+    try:
+        step_fn()
+        torch.cuda.synchronize()
+    finally:
+        L.call = orig
+    out = {}
+    for kind in ("pmfb_conv_fwd", "pmfb_conv_wgrad"):
+        sel = [(f, e0.elapsed_time(e1)) for (n, f, e0, e1) in recs if n == kind]
+        if not sel:
+            continue
+        fl, t = sum(f for f, _ in sel), sum(ms for _, ms in sel)
+        out[kind] = {"launches": len(sel), "gflop": fl / 1e9, "ms": t, "tflops": fl / (t * 1e-3) / 1e12}
+    dom = out.get("pmfb_conv_fwd")
+    if not dom:
+        return None
+    return {"bound": "tensor", "kernel": "conv_fwd_tc_kernel (tcgen05 kind::tf32 implicit GEMM: forward + dgrad launches)",
+            "achieved": dom["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": dom["tflops"] / peak_tf,
+            "peak_source": peak_src + "; kind::tf32 issues at half the bf16 rate, so 0.5 is this kernel's ceiling",
+            "traffic": None, "launches_per_step": dom["launches"], "ms_in_kernel_per_step": dom["ms"],
+            "share_of_step": dom["ms"] / ms_per_step,
+            "wgrad": out.get("pmfb_conv_wgrad")}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
