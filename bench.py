@@ -295,39 +295,56 @@ def run_ours(args):
 
 
 def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
-    """Time every pmfb_conv_fwd launch (forward convs and dgrads) of one step with CUDA events on the launching
-    stream; algorithmic FLOPs per launch = 2 * pixels * c_out * c_in * taps."""
+    """One extra, eagerly launched step (CUDA graphs off) with CUDA events around EVERY C-ABI call on the launching
+    stream: per-entry-point device time, and for the tcgen05 conv kernels the algorithmic FLOPs per launch
+    (2 * pixels * c_out * c_in * taps)."""
     from pmf_b200 import _lib as L
-    import ctypes as C
     recs = []
     orig = L.call
 
     def call(name, *a):
-        if name not in ("pmfb_conv_fwd", "pmfb_conv_wgrad"):
-            return orig(name, *a)
-        d = a[0]._obj
-        flops = 2.0 * d.n_batch * d.out_h * d.out_w * d.c_out * d.c_in * d.n_taps
-        if d.n_taps == 7 and d.c_in == 32:
-            flops *= 21.0 / 32.0  # the 7x7x3 stem runs as 7 taps over 21 real (+11 zero) unrolled channels
+        flops = 0.0
+        if name in ("pmfb_conv_fwd", "pmfb_conv_wgrad"):
+            d = a[0]._obj
+            flops = 2.0 * d.n_batch * d.out_h * d.out_w * d.c_out * d.c_in * d.n_taps
+            if d.n_taps == 7 and d.c_in == 32:
+                flops *= 21.0 / 32.0  # the 7x7x3 stem runs as 7 taps over 21 real (+11 zero) unrolled channels
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         orig(name, *a)
         e1.record()
         recs.append((name, flops, e0, e1))
 
-    L.call = call
+    prev = os.environ.get("PMFB_CUDA_GRAPH")
+    os.environ["PMFB_CUDA_GRAPH"] = "0"
     try:
+        step_fn()  # eager warm-up (allocator)
+        torch.cuda.synchronize()
+        L.call = call
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_a.record()
         step_fn()
+        e_b.record()
         torch.cuda.synchronize()
     finally:
         L.call = orig
+        if prev is None:
+            os.environ.pop("PMFB_CUDA_GRAPH", None)
+        else:
+            os.environ["PMFB_CUDA_GRAPH"] = prev
+    by = {}
+    for (n, f, e0, e1) in recs:
+        r = by.setdefault(n, [0, 0.0, 0.0])
+        r[0] += 1
+        r[1] += e0.elapsed_time(e1)
+        r[2] += f
+    breakdown = {n.replace("pmfb_", ""): {"launches": r[0], "ms": round(r[1], 3)} for n, r in sorted(by.items(), key=lambda kv: -kv[1][1])}
+    in_kernels = sum(r[1] for r in by.values())
     out = {}
     for kind in ("pmfb_conv_fwd", "pmfb_conv_wgrad"):
-        sel = [(f, e0.elapsed_time(e1)) for (n, f, e0, e1) in recs if n == kind]
-        if not sel:
-            continue
-        fl, t = sum(f for f, _ in sel), sum(ms for _, ms in sel)
-        out[kind] = {"launches": len(sel), "gflop": fl / 1e9, "ms": t, "tflops": fl / (t * 1e-3) / 1e12}
+        if kind in by:
+            c, t, fl = by[kind]
+            out[kind] = {"launches": c, "gflop": fl / 1e9, "ms": t, "tflops": fl / (t * 1e-3) / 1e12}
     dom = out.get("pmfb_conv_fwd")
     if not dom:
         return None
@@ -335,8 +352,9 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
             "achieved": dom["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": dom["tflops"] / peak_tf,
             "peak_source": peak_src + "; kind::tf32 issues at half the bf16 rate, so 0.5 is this kernel's ceiling",
             "traffic": None, "launches_per_step": dom["launches"], "ms_in_kernel_per_step": dom["ms"],
-            "share_of_step": dom["ms"] / ms_per_step,
-            "wgrad": out.get("pmfb_conv_wgrad")}
+            "share_of_step": dom["ms"] / max(in_kernels, 1e-9),
+            "wgrad": out.get("pmfb_conv_wgrad"), "cabi_ms_per_step": in_kernels,
+            "eager_step_ms": e_a.elapsed_time(e_b), "breakdown": breakdown}
 
 
 def main():

@@ -198,18 +198,30 @@ def _pick_tile(h, w, total):
 
 
 class WeightCache:
-    """Packed tf32 copies of the conv weights, re-packed when the parameter's version or storage changes."""
+    """Packed tf32 copies of the conv weights.  Eager mode: re-packed when the parameter's version or storage changes.
+    Graph mode (``always=True``): packed once per pass (``begin_pass``) unconditionally, so that the pack kernels are
+    part of the captured graph and every replay re-reads the live parameters."""
 
-    def __init__(self):
+    def __init__(self, always=False):
         self.entries = {}
+        self.always = always
+        self.epoch = 0
+
+    def begin_pass(self):
+        self.epoch += 1
 
     def get(self, cp, need_dgrad, stream):
         w = cp.weight
         key = cp.name
-        tag = (w.data_ptr(), w._version, None if cp.bias is None else (cp.bias.data_ptr(), cp.bias._version), need_dgrad)
         e = self.entries.get(key)
-        if e is not None and e["tag"] == tag:
-            return e
+        if self.always:
+            tag = ("epoch", self.epoch)
+            if e is not None and e["tag"] == tag and (e["dgrad"] is not None or not need_dgrad):
+                return e
+        else:
+            tag = (w.data_ptr(), w._version, None if cp.bias is None else (cp.bias.data_ptr(), cp.bias._version), need_dgrad)
+            if e is not None and e["tag"] == tag:
+                return e
         dev = w.device
         if e is None or e["fwd"].device != dev or (need_dgrad and e["dgrad"] is None):
             e = {"fwd": torch.empty(cp.taps * cp.c_out_p * cp.c_in_p, device=dev, dtype=torch.float32),
@@ -271,15 +283,23 @@ class Engine:
             raise NotImplementedError("pmf_b200: backward is implemented for train-mode (batch-statistics) BatchNorm only; "
                                       "call .train() or run the eval forward under torch.no_grad()")
         self.cache = cache
+        self.cache.begin_pass()
         self.st = torch.cuda.current_stream(device).cuda_stream
         self.tape = []
         self.dropout = dropout  # see mask_for
         self.d64 = _Scratch(torch.float64, 1 << 17, device, self.st, zero=True)
         self.f32 = _Scratch(torch.float32, 1 << 17, device, self.st, zero=False)
         self.param_grads = {}
+        self.flat_views = None  # graph mode: {param name: view into one flat gradient buffer}
         self.nbt_list = []
 
     # ------------------------------------------------------------------------------------------ helpers
+    def _pgrad(self, name, like):
+        """Storage for one parameter gradient (a view of the flat buffer in graph mode)."""
+        if self.flat_views is not None:
+            return self.flat_views[name]
+        return torch.empty_like(like, memory_format=torch.contiguous_format)
+
     def new(self, n, h, w, c, needs_grad=True):
         return Act(torch.empty((n, h, w, c), device=self.device, dtype=torch.float32), needs_grad=needs_grad)
 
@@ -405,7 +425,7 @@ class Engine:
         d.ksplit = max(1, min(max(1, total_pt // 4), (2 * N_SM + base - 1) // base))
         d.dw = packed.data_ptr()
         L.call("pmfb_conv_wgrad", C.byref(d), self.st)
-        gw = torch.empty_like(cp.weight, memory_format=torch.contiguous_format)
+        gw = self._pgrad(cp.name + ".weight", cp.weight)
         L.call("pmfb_unpack_wgrad", packed.data_ptr(), cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0, cp.c_out_p,
                cp.c_in_p, gw.data_ptr(), 0, self.st)
         self.param_grads[cp.name + ".weight"] = gw
@@ -438,7 +458,7 @@ class Engine:
                                   self._epi(r1=sub if acc else None, rnd=rnd))
 
     def _bias_grad(self, cp, colsum64):
-        gb = torch.empty_like(cp.bias)
+        gb = self._pgrad(cp.name + ".bias", cp.bias)
         L.call("pmfb_d2f", colsum64.data_ptr(), gb.data_ptr(), cp.c_out, 1.0, 0, 0, self.st)
         self.param_grads[cp.name + ".bias"] = gb
 
@@ -475,7 +495,7 @@ class Engine:
                invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), n, h, w, c, red.data_ptr(), self.st)
         d_pre = torch.empty((n, h, w, c), device=self.device, dtype=torch.float32)
         cs = self.d64.take(c) if want_colsum else None
-        gw, gb = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
+        gw, gb = self._pgrad(bn.name + ".weight", bn.weight), self._pgrad(bn.name + ".bias", bn.bias)
         L.call("pmfb_bn_bwd_apply", C.byref(dyv), C.byref(mulv), C.byref(zv), act_z, C.byref(xv), mean.data_ptr(),
                invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), bn.weight.detach().data_ptr(), red.data_ptr(), leaky_x,
                n, h, w, c, d_pre.data_ptr(), d_pre.stride(0), d_pre.stride(1), d_pre.stride(2), 1, gw.data_ptr(),
@@ -713,13 +733,18 @@ class Engine:
         return out
 
     def softmax_backward(self, logits, probs, dprobs):
-        n, h, w, _ = logits.shape
-        if not dprobs.is_contiguous():
-            dprobs = dprobs.contiguous()
+        """d logits from d probs (both dense NCHW) into the logits' gradient buffer; returns that buffer."""
         g, acc = logits.grad_target()
         assert not acc
+        self.softmax_backward_into(g, probs, dprobs)
+        return g
+
+    def softmax_backward_into(self, g, probs, dprobs, stream=None):
+        n, h, w, _ = g.shape
+        if not dprobs.is_contiguous():
+            dprobs = dprobs.contiguous()
         L.call("pmfb_softmax_nchw_bwd", probs.data_ptr(), dprobs.data_ptr(), n, h, w, probs.shape[1], g.data_ptr(), g.stride(0),
-               g.stride(1), g.stride(2), 1, self.st)
+               g.stride(1), g.stride(2), 1, self.st if stream is None else stream)
 
     # ------------------------------------------------------------------------------------------ tape
     def finish_forward(self):

@@ -11,6 +11,8 @@ optimisers, DDP, ``replaceBN`` and ``load_state_dict`` see the tree they expect)
 called: the whole network runs as one autograd.Function over pmf_b200.engine.  There is no CPU path — calling a
 module with CPU tensors raises.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -271,6 +273,100 @@ class _PMFFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
+class _GraphedPMF:
+    """One (shape, mode, parameter-storage) specialisation of PMFNet captured into CUDA graphs.
+
+    The executor issues ~4000 C-ABI launches per training step; replaying them from two CUDA graphs (forward,
+    backward) removes the Python/ctypes time from the step.  Only three things stay outside the graphs because they
+    touch caller-owned memory whose address changes every call: packing the NCHW inputs, reading d(probabilities)
+    in the softmax backward, and cloning the outputs / parameter gradients handed back to autograd.
+    Weight packing, BatchNorm running-statistic updates and Dropout2d mask draws are graph nodes, so every replay
+    sees the live parameters, updates the live buffers and draws fresh masks (torch's graph-safe Philox)."""
+
+    def __init__(self, mod, pcd, img, record):
+        self.mod = mod
+        self.record = record
+        self.dev = pcd.device
+        n, c_pcd, h, w = pcd.shape
+        self.shape = (n, c_pcd, h, w)
+        self.cache = WeightCache(always=True)
+        self.E = None
+        self.version = 0
+        self.bwd_captured = False
+        self.pool = torch.cuda.graph_pool_handle()
+        self.g_fwd = torch.cuda.CUDAGraph()
+        self.g_bwd = torch.cuda.CUDAGraph() if record else None
+        self.names = [nm for nm, _ in mod.named_parameters()]
+        # static packed inputs (filled eagerly before every replay)
+        self.E_in = Engine(G.ModuleParams(mod), self.dev, mod.training, False, WeightCache(), dropout=False)
+        self.img7 = self.E_in.new(n, h, w, 32, needs_grad=False)
+        self.pcd = self.E_in.new(n, h, w, (c_pcd + 3) // 4 * 4, needs_grad=False)
+        self._stage_inputs(pcd, img)
+        torch.cuda.synchronize(self.dev)
+        with torch.cuda.graph(self.g_fwd, pool=self.pool):
+            E = Engine(G.ModuleParams(mod), self.dev, mod.training, record, self.cache, dropout=mod._dropout_masks())
+            self.lidar, self.camera, self.ll, self.cl = G.pmf_forward_packed(E, self.pcd, self.img7, mod.image_backbone,
+                                                                             mod.nclasses)
+        self.E = E
+        self.ll_grad = self.cl_grad = None
+        # all parameter gradients live in ONE flat buffer: a single clone per step hands them to autograd
+        offs, total = {}, 0
+        for nm, p in mod.named_parameters():
+            offs[nm] = (total, p.numel(), tuple(p.shape))
+            total += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(total, device=self.dev, dtype=torch.float32)
+        self.offs = offs
+        E.flat_views = {nm: self.flat[o:o + k].view(shp) for nm, (o, k, shp) in offs.items()}
+
+    def _stage_inputs(self, pcd, img):
+        self.E_in.st = torch.cuda.current_stream(self.dev).cuda_stream
+        self.E_in.input_nchw(img, 32, n_shift=7, out=self.img7)
+        self.E_in.input_nchw(pcd, self.pcd.c, out=self.pcd)
+
+    def forward(self, pcd, img):
+        self._stage_inputs(pcd, img)
+        self.g_fwd.replay()
+        self.version += 1
+        return self.lidar.clone(), self.camera.clone()
+
+    def backward(self, d_lidar, d_camera):
+        E = self.E
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        if not self.bwd_captured:
+            self.ll_grad, _ = self.ll.grad_target()
+            self.cl_grad, _ = self.cl.grad_target()
+        E.softmax_backward_into(self.ll_grad, self.lidar, d_lidar, stream=st)
+        E.softmax_backward_into(self.cl_grad, self.camera, d_camera, stream=st)
+        if not self.bwd_captured:
+            torch.cuda.synchronize(self.dev)
+            with torch.cuda.graph(self.g_bwd, pool=self.pool):
+                self.grads = E.run_backward()
+            self.bwd_captured = True
+        self.g_bwd.replay()
+        out = self.flat.clone()
+        return tuple(out[o:o + k].view(shp) if nm in self.grads else None
+                     for nm, (o, k, shp) in ((nm, self.offs[nm]) for nm in self.names))
+
+
+class _PMFGraphFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, pcd, img, *params):
+        lidar, camera = runner.forward(pcd, img)
+        ctx.runner, ctx.version = runner, runner.version
+        return lidar, camera
+
+    @staticmethod
+    def backward(ctx, d_lidar, d_camera):
+        r = ctx.runner
+        if not r.record:
+            raise RuntimeError("pmf_b200: backward through a forward that was run without gradient recording")
+        if ctx.version != r.version:
+            raise RuntimeError("pmf_b200: this forward's activations were overwritten by a later forward of the same "
+                               "CUDA-graph specialisation; set PMFB_CUDA_GRAPH=0 for call patterns other than "
+                               "forward -> backward")
+        return (None, None, None) + r.backward(d_lidar, d_camera)
+
+
 class PMFNet(nn.Module):
     """pmf_net.py:224-249.  forward returns the two softmax probability maps (B, nclasses, H, W)."""
 
@@ -286,6 +382,8 @@ class PMFNet(nn.Module):
         self.image_backbone = image_backbone
         self._cache = WeightCache()
         self._dropout_override = None  # tests: False (off) or {site: (N,C) mask}
+        self._graphs = {}
+        self._seen = set()
 
     def _dropout_masks(self):
         if self._dropout_override is not None:
@@ -295,10 +393,30 @@ class PMFNet(nn.Module):
         # honour per-module .eval() on the Dropout2d children (sites whose module is in eval mode are skipped)
         return _DropoutSites(self)
 
+    def _graph_key(self, pcd, img, record, params):
+        drop = tuple((n, m.training, m.p) for n, m in self.named_modules() if isinstance(m, nn.Dropout2d))
+        ptrs = tuple(p.data_ptr() for p in params) + tuple(b.data_ptr() for b in self.buffers())
+        return (tuple(pcd.shape), tuple(img.shape), str(pcd.device), self.training, record, drop, ptrs,
+                tuple(p.requires_grad for p in params))
+
     def forward(self, pcd_feature, img_feature):
         _require_cuda(pcd_feature, img_feature)
+        G.check_input_size(img_feature)
         params = [p for _, p in self.named_parameters()]
         record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        use_graph = (os.environ.get("PMFB_CUDA_GRAPH", "1") != "0" and self._dropout_override is None
+                     and not torch.cuda.is_current_stream_capturing())
+        if use_graph:
+            key = self._graph_key(pcd_feature, img_feature, record, params)
+            runner = self._graphs.get(key)
+            if runner is None and key in self._seen:  # second call with this specialisation: capture it
+                if len(self._graphs) >= 4:
+                    self._graphs.clear()
+                torch.cuda.empty_cache()
+                runner = self._graphs[key] = _GraphedPMF(self, pcd_feature, img_feature, record)
+            self._seen.add(key)
+            if runner is not None:
+                return _PMFGraphFn.apply(runner, pcd_feature, img_feature, *params)
         return _PMFFn.apply(self, record, pcd_feature, img_feature, *params)
 
 

@@ -190,14 +190,23 @@ def rgb_decoder(E, feats, p):
     return E.conv_act(x, p + ".conv", ACT_NONE, rnd=False)
 
 
+def check_input_size(img_feature):
+    h, w = img_feature.shape[2], img_feature.shape[3]
+    if h % 16 != 0 or w % 16 != 0:
+        assert False, "invalid input size: {}".format(img_feature.shape)  # pmf_net.py:87-88
+
+
 def pmf_forward(E, pcd_feature, img_feature, backbone, nclasses):
     """PMFNet.forward, pmf_net.py:242-249.  Inputs are NCHW torch tensors (any strides); returns
     (lidar_probs, camera_probs, lidar_logits_act, camera_logits_act)."""
-    n, c_pcd, h, w = pcd_feature.shape
-    if h % 16 != 0 or w % 16 != 0:
-        assert False, "invalid input size: {}".format(img_feature.shape)  # pmf_net.py:87-88
+    check_input_size(img_feature)
     img7 = E.input_nchw(img_feature, 32, n_shift=7)
-    pcd = E.input_nchw(pcd_feature, (c_pcd + 3) // 4 * 4)
+    pcd = E.input_nchw(pcd_feature, (pcd_feature.shape[1] + 3) // 4 * 4)
+    return pmf_forward_packed(E, pcd, img7, backbone, nclasses)
+
+
+def pmf_forward_packed(E, pcd, img7, backbone, nclasses):
+    """The graph proper, from the packed NHWC inputs (pcd: channel-padded; img7: horizontally unrolled RGB)."""
     feats = resnet_encoder(E, img7, "camera_stream_encoder", backbone)
     lidar_logits = salsanext_fusion(E, pcd, feats, "lidar_stream", nclasses)
     camera_logits = rgb_decoder(E, feats, "camera_stream_decoder")
