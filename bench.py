@@ -314,7 +314,12 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
         orig(name, *a)
         e1.record()
         recs.append((name, flops, e0, e1))
+        if flops:
+            shapes.append("%s n%d %dx%d cin%d cout%d taps%d" % (name[5:], d.n_batch, d.out_h, d.out_w, d.c_in, d.c_out, d.n_taps))
+        else:
+            shapes.append(None)
 
+    shapes = []
     prev = os.environ.get("PMFB_CUDA_GRAPH")
     os.environ["PMFB_CUDA_GRAPH"] = "0"
     try:
@@ -340,6 +345,12 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
         r[2] += f
     breakdown = {n.replace("pmfb_", ""): {"launches": r[0], "ms": round(r[1], 3)} for n, r in sorted(by.items(), key=lambda kv: -kv[1][1])}
     in_kernels = sum(r[1] for r in by.values())
+    convs = sorted(((e0.elapsed_time(e1), f, sh) for (n, f, e0, e1), sh in zip(recs, shapes) if sh), reverse=True)
+    top = [{"ms": round(t, 3), "tflops": round(f / (t * 1e-3) / 1e12, 1), "launch": sh} for t, f, sh in convs[:24]]
+    if os.environ.get("PMFB_BENCH_DUMP"):
+        with open(os.environ["PMFB_BENCH_DUMP"], "w") as fdump:
+            for t, f, sh in convs:
+                fdump.write("%.3f ms  %7.1f TFLOP/s  %s\n" % (t, f / (t * 1e-3) / 1e12, sh))
     out = {}
     for kind in ("pmfb_conv_fwd", "pmfb_conv_wgrad"):
         if kind in by:
@@ -354,7 +365,7 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
             "traffic": None, "launches_per_step": dom["launches"], "ms_in_kernel_per_step": dom["ms"],
             "share_of_step": dom["ms"] / max(in_kernels, 1e-9),
             "wgrad": out.get("pmfb_conv_wgrad"), "cabi_ms_per_step": in_kernels,
-            "eager_step_ms": e_a.elapsed_time(e_b), "breakdown": breakdown}
+            "eager_step_ms": e_a.elapsed_time(e_b), "breakdown": breakdown, "top_conv_launches": top}
 
 
 def main():

@@ -1,0 +1,366 @@
+// conv_fwd_halo_kernel — second-generation implicit-GEMM convolution for the stride-1 layers (forward and dgrad).
+//
+// Why: in the tap-per-TMA kernel (conv_tc.cu) every tap re-fetches the whole 128-pixel input box from L2, so a
+// 3x3 layer moves 9x its input over the L2->SM fabric; ncu showed the 32/64-channel full-resolution layers
+// latency/L2 bound (tensor pipe 2-7 %, DRAM 9-25 %).  Here a CTA loads, per 32-channel slab, ONE halo tile
+//   (16*MT + 2*hy) x (8 + 2*hx) pixels x 32 ch   (one TMA box, 128B-swizzled, zero-filled outside the image)
+// and forms the A operand of every tap by POINTING the UMMA shared-memory descriptor at a shifted window of that
+// tile: with an 8-pixel-wide output tile every 8-row swizzle atom is one output row, so consecutive atoms are a
+// constant (8 + 2*hx)*128 bytes apart (the descriptor's stride-byte-offset) for every tap.  Only the weights stream
+// per tap.  The kernel is persistent (one CTA per SM walks the tile list), keeps up to two accumulator sets in TMEM so
+// the epilogue of tile i overlaps the MMAs of tile i+1, and processes MT stacked 128-pixel tiles per weight fetch.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5 epilogue.
+#include <stdlib.h>
+
+#include "common.h"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace pmfb {
+
+constexpr int kHThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int kHEpiWarps = 8;
+constexpr int kHMaxC = 512;       // per-channel epilogue vectors staged in shared memory
+constexpr int kHCtrlBytes = 1024 + 4 * kHMaxC * 4;
+constexpr int kHMaxB = 8;
+constexpr int kHSmemBudget = 208 * 1024;
+
+struct HCtrl {
+  uint64_t full_a[2], empty_a[2];
+  uint64_t full_b[kHMaxB], empty_b[kHMaxB];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+struct HaloK {
+  int n_taps, ks;
+  int tap_dw[PMFB_MAX_TAPS], tap_dh[PMFB_MAX_TAPS], tap_wi[PMFB_MAX_TAPS];
+  int hx, hy, mt;
+  int tiles_x, tiles_y, n_batch, n_blocks;
+  int out_h, out_w, c_out, n_tile;
+  int nsb, a_bytes, a_box_bytes, nacc, tmem_cols, use_base_off;
+  float* out;
+  long long o_sn, o_sy, o_sx;
+  EpiParams epi;
+};
+
+__device__ __forceinline__ uint64_t desc_with_base(uint32_t saddr, uint32_t lbo, uint32_t sbo, int use_base_off) {
+  uint64_t d = make_smem_desc(saddr, lbo, sbo, 2u);
+  if (use_base_off) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
+  return d;
+}
+
+__global__ void __launch_bounds__(kHThreads, 1)
+conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
+                     const __grid_constant__ HaloK P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  HCtrl* ctrl = reinterpret_cast<HCtrl*>(smem);
+  uint8_t* a_buf = smem + kHCtrlBytes;
+  uint8_t* b_buf = a_buf + 2 * (size_t)P.a_bytes;
+  const int b_bytes = P.n_tile * 128;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform -> uniform datapath
+  const int lane = threadIdx.x & 31;
+  const int total = P.tiles_x * P.tiles_y * P.n_batch * P.n_blocks;
+  const int th = 16 * P.mt;          // CTA tile height in pixels
+  const int pitch = 8 + 2 * P.hx;    // halo tile row pitch in pixels
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctrl->full_a[i], 1);
+      mbar_init(&ctrl->empty_a[i], 1);
+      mbar_init(&ctrl->tmem_full[i], 1);
+      mbar_init(&ctrl->tmem_empty[i], kHEpiWarps);
+    }
+    for (int i = 0; i < P.nsb; ++i) {
+      mbar_init(&ctrl->full_b[i], 1);
+      mbar_init(&ctrl->empty_b[i], 1);
+    }
+    fence_mbar_init();
+    fence_proxy_async();
+    tma_prefetch_desc(&tmx);
+    tma_prefetch_desc(&tmw);
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctrl->tmem_base, (uint32_t)P.tmem_cols);
+    tmem_relinquish();
+  }
+  {
+    float* sv = reinterpret_cast<float*>(smem + 1024);
+    const float* src[4] = {P.epi.alpha1, P.epi.beta1, P.epi.alpha2, P.epi.beta2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (src[k])
+        for (int c = threadIdx.x; c < P.c_out; c += kHThreads) sv[k * kHMaxC + c] = __ldg(src[k] + c);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        int r = w;
+        const int nb = r % P.n_blocks; r /= P.n_blocks;
+        const int tx = r % P.tiles_x; r /= P.tiles_x;
+        const int ty = r % P.tiles_y;
+        const int n_img = r / P.tiles_y;
+        const int x0 = tx * 8, y0 = ty * th, n0 = nb * P.n_tile;
+        for (int s = 0; s < P.ks; ++s) {
+          const uint32_t ab = a_it & 1u;
+          mbar_wait(&ctrl->empty_a[ab], ((a_it >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&ctrl->full_a[ab], (uint32_t)P.a_box_bytes);
+          tma_load_5d(a_buf + (size_t)ab * P.a_bytes, &tmx, &ctrl->full_a[ab], s * 32, x0 - P.hx, 0, y0 - P.hy, n_img);
+          ++a_it;
+          for (int t = 0; t < P.n_taps; ++t) {
+            const uint32_t st = b_it % (uint32_t)P.nsb;
+            mbar_wait(&ctrl->empty_b[st], ((b_it / (uint32_t)P.nsb) & 1u) ^ 1u);
+            mbar_expect_tx(&ctrl->full_b[st], (uint32_t)b_bytes);
+            tma_load_3d(b_buf + (size_t)st * b_bytes, &tmw, &ctrl->full_b[st], s * 32, n0, P.tap_wi[t]);
+            ++b_it;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------- MMA issuer.  The WHOLE warp walks the loops so that every descriptor lives in uniform registers
+    // (ncu: with a single divergent lane the ~20 integer instructions that rebuilt the two 64-bit descriptors for each
+    // UTCHMMA made instruction issue, not the tensor pipe, the limiter); only the tcgen05 instructions are predicated
+    // on one lane.  Descriptors are (constant high word | low word), and the low word advances by plain adds:
+    // +2 (32 B >> 4) per K step, +(tap row/column offset) per tap, +(16 rows) per stacked tile.
+    const uint32_t idesc = make_idesc_tf32(128, (uint32_t)P.n_tile, 0, 0);
+    const uint32_t sbo = (uint32_t)pitch * 128u;
+    const uint32_t hi_a = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // bits 32..63 of the A descriptor
+    const uint32_t hi_b = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    const uint32_t lbo_lo = (16u >> 4) << 16;
+    const uint32_t j_step = (uint32_t)(16 * pitch * 128) >> 4;
+    uint32_t a_it = 0, b_it = 0, acc_it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++acc_it) {
+      const uint32_t buf = acc_it % (uint32_t)P.nacc;
+      mbar_wait(&ctrl->tmem_empty[buf], ((acc_it / (uint32_t)P.nacc) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + buf * (uint32_t)(P.mt * P.n_tile);
+      uint32_t accumulate = 0;
+      for (int s = 0; s < P.ks; ++s) {
+        const uint32_t ab = a_it & 1u;
+        mbar_wait(&ctrl->full_a[ab], (a_it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t a_lo0 = ((smem_u32(a_buf + (size_t)ab * P.a_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
+        for (int t = 0; t < P.n_taps; ++t) {
+          const uint32_t st = b_it % (uint32_t)P.nsb;
+          mbar_wait(&ctrl->full_b[st], (b_it / (uint32_t)P.nsb) & 1u);
+          tc_fence_after();
+          const uint32_t b_lo = ((smem_u32(b_buf + (size_t)st * b_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
+          uint32_t a_lo = a_lo0 + (uint32_t)((((P.tap_dh[t] + P.hy) * pitch + P.tap_dw[t] + P.hx) * 128) >> 4);
+          uint32_t d_col = d_base;
+          for (int j = 0; j < P.mt; ++j) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = (static_cast<uint64_t>(hi_a) << 32) | (a_lo + 2u * k);
+              const uint64_t bd = (static_cast<uint64_t>(hi_b) << 32) | (b_lo + 2u * k);
+              umma_tf32_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
+            }
+            a_lo += j_step;
+            d_col += (uint32_t)P.n_tile;
+          }
+          accumulate = 1;
+          umma_commit_warp(&ctrl->empty_b[st]);
+          ++b_it;
+        }
+        umma_commit_warp(&ctrl->empty_a[ab]);
+        ++a_it;
+      }
+      umma_commit_warp(&ctrl->tmem_full[buf]);
+    }
+  } else {
+    // ------------- epilogue: 8 warps; warp pair (q, half) shares TMEM lane quadrant q and alternates 32-column units.
+    // Every unit issues its TMEM load and ALL of its residual global loads before the first use (memory-level
+    // parallelism is what bounds the 32/64-channel full-resolution layers), then applies the fused functional with the
+    // per-channel vectors staged in shared memory, and writes one full 128-byte line per thread.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const float* sv = reinterpret_cast<const float*>(smem + 1024);  // [alpha1 | beta1 | alpha2 | beta2] x kHMaxC
+    const bool hA1 = P.epi.alpha1 != nullptr, hB1 = P.epi.beta1 != nullptr, hA2 = P.epi.alpha2 != nullptr,
+               hB2 = P.epi.beta2 != nullptr;
+    const int chunks = (P.n_tile + 31) >> 5;
+    uint32_t acc_it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++acc_it) {
+      int r = w;
+      const int nb = r % P.n_blocks; r /= P.n_blocks;
+      const int tx = r % P.tiles_x; r /= P.tiles_x;
+      const int ty = r % P.tiles_y;
+      const int n_img = r / P.tiles_y;
+      const int x0 = tx * 8, y0 = ty * th, n0 = nb * P.n_tile;
+      const uint32_t buf = acc_it % (uint32_t)P.nacc;
+      mbar_wait_sleep(&ctrl->tmem_full[buf], (acc_it / (uint32_t)P.nacc) & 1u);
+      tc_fence_after();
+      const int row = q * 32 + lane;
+      const int units = P.mt * chunks;
+      for (int u = half; u < units; u += 2) {
+        const int j = u / chunks, ch = u - j * chunks;
+        const int y = y0 + 16 * j + (row >> 3), x = x0 + (row & 7);
+        const bool valid = (y < P.out_h) && (x < P.out_w);
+        const int c0 = n0 + ch * 32;                       // first channel of this unit
+        const int ncol = min(32, P.n_tile - ch * 32);      // 32 or 16
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(P.mt * P.n_tile) +
+                               (uint32_t)(j * P.n_tile + ch * 32);
+        float v[32];
+        tmem_ld16(taddr, v);
+        if (ncol > 16) tmem_ld16(taddr + 16, v + 16);
+        const long long pix_o = (long long)n_img * P.o_sn + (long long)y * P.o_sy + (long long)x * P.o_sx;
+        float4 r1v[8], mulv[8], r2v[8];
+        const EpiPixel ep = epi_pixel(P.epi, n_img, y, x);
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = c0 + 4 * i;
+            const bool on = (4 * i < ncol) && (c < P.c_out);
+            if (ep.r1 && on) r1v[i] = ld4(ep.r1 + c);
+            if (ep.mul && on) mulv[i] = ld4(ep.mul + c);
+            if (ep.r2 && on) r2v[i] = ld4(ep.r2 + c);
+          }
+        }
+        tmem_ld_wait();
+        if (valid) {
+          float* optr = P.out + pix_o;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = c0 + 4 * i;
+            if ((4 * i < ncol) && (c < P.c_out)) {
+              float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              if (hA1) { const float4 a = *reinterpret_cast<const float4*>(sv + c); o.x *= a.x; o.y *= a.y; o.z *= a.z; o.w *= a.w; }
+              if (hB1) { const float4 b = *reinterpret_cast<const float4*>(sv + kHMaxC + c); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+              if (ep.r1) { o.x += r1v[i].x; o.y += r1v[i].y; o.z += r1v[i].z; o.w += r1v[i].w; }
+              if (P.epi.act) { o.x = epi_act(P.epi.act, o.x); o.y = epi_act(P.epi.act, o.y); o.z = epi_act(P.epi.act, o.z); o.w = epi_act(P.epi.act, o.w); }
+              if (hA2) { const float4 a = *reinterpret_cast<const float4*>(sv + 2 * kHMaxC + c); o.x *= a.x; o.y *= a.y; o.z *= a.z; o.w *= a.w; }
+              if (hB2) { const float4 b = *reinterpret_cast<const float4*>(sv + 3 * kHMaxC + c); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+              if (ep.mul) { o.x *= mulv[i].x; o.y *= mulv[i].y; o.z *= mulv[i].z; o.w *= mulv[i].w; }
+              if (ep.r2) { o.x += r2v[i].x; o.y += r2v[i].y; o.z += r2v[i].z; o.w += r2v[i].w; }
+              if (P.epi.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+              *reinterpret_cast<float4*>(optr + c) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctrl->tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+static int pow2_cols_h(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+// Returns 1 if the descriptor can run on the halo kernel (stride-1 source, taps inside a small halo).
+int halo_eligible(const pmfb_conv_desc* d) {
+  if (d->x.dims[2] != 1) return 0;
+  int hx = 0, hy = 0;
+  for (int i = 0; i < d->n_taps; ++i) {
+    if (d->tap_dp[i] != 0 || d->tap_dc[i] != 0) return 0;
+    const int ax = d->tap_dw[i] < 0 ? -d->tap_dw[i] : d->tap_dw[i];
+    const int ay = d->tap_dh[i] < 0 ? -d->tap_dh[i] : d->tap_dh[i];
+    if (ax > hx) hx = ax;
+    if (ay > hy) hy = ay;
+  }
+  return (hx <= 2 && hy <= 3 && d->c_out <= kHMaxC) ? 1 : 0;
+}
+
+int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
+  static int sm_count = 0;
+  static int base_off_mode = -1;
+  if (sm_count == 0) {
+    int dev = 0;
+    PMFB_CUDA_CHECK(cudaGetDevice(&dev));
+    PMFB_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    const char* e = getenv("PMFB_HALO_BASEOFF");
+    base_off_mode = e ? atoi(e) : 0;  // measured on B200: the 128B swizzle is a pure function of the smem address, no base offset needed
+  }
+  HaloK P;
+  P.n_taps = d->n_taps;
+  P.ks = (d->c_in + 31) / 32;
+  P.hx = P.hy = 0;
+  for (int i = 0; i < PMFB_MAX_TAPS; ++i) {
+    P.tap_dw[i] = d->tap_dw[i];
+    P.tap_dh[i] = d->tap_dh[i];
+    P.tap_wi[i] = d->use_tap_wi ? d->tap_wi[i] : i;
+    if (i < d->n_taps) {
+      const int ax = d->tap_dw[i] < 0 ? -d->tap_dw[i] : d->tap_dw[i];
+      const int ay = d->tap_dh[i] < 0 ? -d->tap_dh[i] : d->tap_dh[i];
+      if (ax > P.hx) P.hx = ax;
+      if (ay > P.hy) P.hy = ay;
+    }
+  }
+  int n_tile = d->c_out < 256 ? ((d->c_out + 15) / 16) * 16 : 256;
+  P.n_tile = n_tile;
+  P.n_blocks = (d->c_out + n_tile - 1) / n_tile;
+  P.c_out = d->c_out;
+  P.out_h = d->out_h;
+  P.out_w = d->out_w;
+  P.n_batch = d->n_batch;
+  P.tiles_x = (d->out_w + 7) / 8;
+  // MT: two stacked 128-pixel tiles per weight fetch when that still leaves a full wave of work
+  int mt = 2;
+  {
+    const long long items2 = (long long)P.tiles_x * ((d->out_h + 31) / 32) * d->n_batch * P.n_blocks;
+    if (items2 < sm_count || 2 * n_tile > 512) mt = 1;
+  }
+  P.mt = mt;
+  P.tiles_y = (d->out_h + 16 * mt - 1) / (16 * mt);
+  P.nacc = (2 * mt * n_tile <= 512) ? 2 : 1;
+  P.tmem_cols = pow2_cols_h(P.nacc * mt * n_tile);
+  const int rows = 16 * mt + 2 * P.hy, pitch = 8 + 2 * P.hx;
+  P.a_box_bytes = rows * pitch * 128;
+  P.a_bytes = (P.a_box_bytes + 1023) & ~1023;
+  const int b_bytes = n_tile * 128;
+  int nsb = (kHSmemBudget - kHCtrlBytes - 2 * P.a_bytes) / b_bytes;
+  if (nsb > kHMaxB) nsb = kHMaxB;
+  if (nsb < 2) return fail(PMFB_ERR_INVALID, "conv halo: shared memory budget exceeded (n_tile=%d)", n_tile);
+  if (d->c_out > kHMaxC) return fail(PMFB_ERR_INVALID, "conv halo: c_out=%d > %d", d->c_out, kHMaxC);
+  P.nsb = nsb;
+  P.use_base_off = base_off_mode;
+  P.out = d->out;
+  P.o_sn = d->o_sn;
+  P.o_sy = d->o_sy;
+  P.o_sx = d->o_sx;
+  int rc = epi_from_c(&d->epi, &P.epi);
+  if (rc) return rc;
+
+  CUtensorMap tmx, tmw;
+  uint32_t boxx[5] = {32, (uint32_t)pitch, 1, (uint32_t)rows, 1};
+  rc = make_tmap_f32(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, boxx);
+  if (rc) return rc;
+  int n_slabs = d->n_taps;
+  if (d->use_tap_wi)
+    for (int i = 0; i < d->n_taps; ++i)
+      if (d->tap_wi[i] + 1 > n_slabs) n_slabs = d->tap_wi[i] + 1;
+  uint64_t wdims[3] = {(uint64_t)d->c_in, (uint64_t)d->c_out, (uint64_t)n_slabs};
+  uint64_t wstr[2] = {(uint64_t)d->c_in * 4, (uint64_t)d->c_in * d->c_out * 4};
+  uint32_t boxw[3] = {32, (uint32_t)n_tile, 1};
+  rc = make_tmap_f32(&tmw, d->w, 3, wdims, wstr, boxw);
+  if (rc) return rc;
+
+  const size_t smem = (size_t)kHCtrlBytes + 2 * (size_t)P.a_bytes + (size_t)nsb * b_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PMFB_CUDA_CHECK(cudaFuncSetAttribute(conv_fwd_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemBudget + 2048));
+    attr_set = true;
+  }
+  const long long total = (long long)P.tiles_x * P.tiles_y * P.n_batch * P.n_blocks;
+  const int grid = (int)(total < sm_count ? total : sm_count);
+  conv_fwd_halo_kernel<<<grid, kHThreads, smem, (cudaStream_t)stream>>>(tmx, tmw, P);
+  PMFB_LAUNCH_CHECK("conv_fwd_halo_kernel");
+  return PMFB_OK;
+}
+
+}  // namespace pmfb

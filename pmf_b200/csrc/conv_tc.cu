@@ -17,6 +17,8 @@
 //
 // Reference semantics being replaced: every nn.Conv2d call of pc_processor/models/pmf_net.py and
 // salsanext.py (cuDNN on the reference side); see SURVEY.md Appendix C for the layer list.
+#include <stdlib.h>
+
 #include "common.h"
 #include "epilogue.cuh"
 #include "ptx.cuh"
@@ -306,10 +308,29 @@ static const int kSmemBudget = 200 * 1024;
 
 }  // namespace pmfb
 
+namespace pmfb {
+int halo_eligible(const pmfb_conv_desc* d);
+int launch_conv_halo(const pmfb_conv_desc* d, void* stream);
+}  // namespace pmfb
+
 using namespace pmfb;
 
 extern "C" int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream) {
   if (!d) return fail(PMFB_ERR_INVALID, "null desc");
+  if (d->n_taps < 1 || d->n_taps > PMFB_MAX_TAPS) return fail(PMFB_ERR_INVALID, "n_taps=%d", d->n_taps);
+  if (d->c_out % 4 || d->c_in % 4) return fail(PMFB_ERR_INVALID, "c_in/c_out must be multiples of 4");
+  if ((d->o_sn | d->o_sy | d->o_sx) % 4 || (reinterpret_cast<uintptr_t>(d->out) & 15))
+    return fail(PMFB_ERR_INVALID, "output view must be 16-byte aligned with strides multiple of 4");
+  {
+    // stride-1 layers with a small tap halo run on the persistent halo-tile kernel (conv_halo.cu); the
+    // tap-per-TMA kernel below keeps the stride-2 (parity-layout) and wide-dilation (ASPP) layers.
+    static int force_v1 = -1;
+    if (force_v1 < 0) {
+      const char* e = getenv("PMFB_CONV_V1");
+      force_v1 = (e && atoi(e)) ? 1 : 0;
+    }
+    if (!force_v1 && halo_eligible(d)) return launch_conv_halo(d, stream);
+  }
   if (d->tile_w * d->tile_h != kTileM) return fail(PMFB_ERR_INVALID, "tile_w*tile_h must be 128");
   if (d->n_tile < 16 || d->n_tile > 256 || d->n_tile % 16)
     return fail(PMFB_ERR_INVALID, "n_tile=%d must be a multiple of 16 in [16,256]", d->n_tile);

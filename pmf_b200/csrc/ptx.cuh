@@ -58,6 +58,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Epilogue-side wait: back off between polls so that idle warps do not burn issue slots next to the MMA issuer.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -108,6 +117,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-collective variants: every lane executes the statement with warp-uniform operands (so ptxas keeps them in
+// uniform registers) and ONE lane, chosen by elect.sync inside the asm, issues the tcgen05 instruction.
+__device__ __forceinline__ void umma_tf32_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
       : "memory");
 }
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread retire.
