@@ -59,7 +59,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
   const int stage_b_bytes = P.n_tile * 128;
   const int stage_bytes = kSlabBytes + stage_b_bytes;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   int bx = blockIdx.x;
@@ -108,25 +108,27 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(kTileM, (uint32_t)P.n_tile, 0, 0);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % P.stages;
-        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-        mbar_wait(&ctrl->full[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + kSlabBytes;
+    // whole warp walks the loop with uniform descriptors; one elected lane issues (see conv_halo.cu)
+    const uint32_t idesc = make_idesc_tf32(kTileM, (uint32_t)P.n_tile, 0, 0);
+    const uint32_t hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    const uint32_t lbo_lo = (16u >> 4) << 16;
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % P.stages;
+      const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
+      mbar_wait(&ctrl->full[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
+      const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | lbo_lo;
+      const uint32_t b_lo = (((a_addr + kSlabBytes) & 0x3FFFFu) >> 4) | lbo_lo;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-          umma_tf32(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&ctrl->empty[s]);
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_lo + 2u * k);
+        const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (b_lo + 2u * k);
+        umma_tf32_warp(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
       }
-      umma_commit(&ctrl->tmem_full);
+      umma_commit_warp(&ctrl->empty[s]);
     }
+    umma_commit_warp(&ctrl->tmem_full);
   } else {
     // ---------------- epilogue: TMEM -> registers -> fused pointwise -> global (NHWC)
     const int q = warp & 3;
@@ -185,7 +187,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
   const int nb_boxes = P.n_tile / 32;
   const int stage_bytes = (4 + nb_boxes) * kBoxBytes;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   const int total_rb = P.n_taps * P.cb_per_tap;
@@ -245,28 +247,29 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = make_idesc_tf32(kTileM, (uint32_t)P.n_tile, 1, 1);
-        for (int it = 0; it < iters; ++it) {
-          const int s = it % P.stages;
-          const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
-          mbar_wait(&ctrl->full[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
-          const uint32_t b_addr = a_addr + 4 * kBoxBytes;
+      const uint32_t idesc = make_idesc_tf32(kTileM, (uint32_t)P.n_tile, 1, 1);
+      // MN-major tf32 operands must use the SWIZZLE_128B_BASE32B layout (layout type 1): 32 channels (128 B)
+      // contiguous per pixel row, 32B chunks XOR-swizzled over 4-row (512 B) atoms.  One K=8 MMA step spans two
+      // atoms (SBO = 512 B); LBO = distance between 32-channel blocks; a K step advances the start by 1024 B.
+      const uint32_t hi = ((512u >> 4) & 0x3FFFu) | (1u << 14) | (1u << 29);
+      const uint32_t lbo_lo = (((uint32_t)kBoxBytes >> 4) & 0x3FFFu) << 16;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % P.stages;
+        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
+        mbar_wait(&ctrl->full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
+        const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | lbo_lo;
+        const uint32_t b_lo = (((a_addr + 4 * kBoxBytes) & 0x3FFFFu) >> 4) | lbo_lo;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // MN-major tf32 operands must use the SWIZZLE_128B_BASE32B layout: 32 channels (128 B)
-            // contiguous per pixel row, 32B chunks XOR-swizzled over 4-row (512 B) atoms.  One K=8
-            // MMA step spans two atoms (SBO = 512 B); LBO = distance between 32-channel blocks.
-            const uint64_t ad = make_smem_desc(a_addr + k * 1024, kBoxBytes, 512, 1u);
-            const uint64_t bd = make_smem_desc(b_addr + k * 1024, kBoxBytes, 512, 1u);
-            umma_tf32(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&ctrl->empty[s]);
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_lo + 64u * k);
+          const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (b_lo + 64u * k);
+          umma_tf32_warp(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&ctrl->tmem_full);
+        umma_commit_warp(&ctrl->empty[s]);
       }
+      umma_commit_warp(&ctrl->tmem_full);
     } else {
       const int q = warp & 3;  // accumulator rows q*32..q*32+31 == row-block q of this CTA
       const int rb = rb0 + q;
@@ -311,6 +314,8 @@ static const int kSmemBudget = 200 * 1024;
 namespace pmfb {
 int halo_eligible(const pmfb_conv_desc* d);
 int launch_conv_halo(const pmfb_conv_desc* d, void* stream);
+int wgrad_halo_eligible(const pmfb_wgrad_desc* d);
+int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream);
 }  // namespace pmfb
 
 using namespace pmfb;
@@ -402,6 +407,16 @@ extern "C" int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream) {
 
 extern "C" int pmfb_conv_wgrad(const pmfb_wgrad_desc* d, void* stream) {
   if (!d) return fail(PMFB_ERR_INVALID, "null desc");
+  if (d->n_taps < 1 || d->n_taps > PMFB_MAX_TAPS) return fail(PMFB_ERR_INVALID, "n_taps=%d", d->n_taps);
+  if (d->c_out % 4 || d->c_in % 4) return fail(PMFB_ERR_INVALID, "c_in/c_out must be multiples of 4");
+  {
+    static int force_v1 = -1;
+    if (force_v1 < 0) {
+      const char* e = getenv("PMFB_WGRAD_V1");
+      force_v1 = (e && atoi(e)) ? 1 : 0;
+    }
+    if (!force_v1 && wgrad_halo_eligible(d)) return launch_wgrad_halo(d, stream);
+  }
   if (d->ptile_w * d->ptile_h != 32) return fail(PMFB_ERR_INVALID, "ptile_w*ptile_h must be 32");
   if (d->n_tile < 32 || d->n_tile > 256 || d->n_tile % 32)
     return fail(PMFB_ERR_INVALID, "n_tile=%d must be a multiple of 32 in [32,256]", d->n_tile);
