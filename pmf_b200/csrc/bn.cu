@@ -14,63 +14,96 @@ namespace pmfb {
 
 constexpr int kRedThreads = 256;
 
+// Pixel-indexed view.  Every activation the executor creates is "pixel-linear" (offset = pixel * sx: dense NHWC or a
+// channel slice of it), which keeps 64-bit divisions out of the inner loops; broadcast (Dropout2d scale) and parity
+// sub-grid views take the general decode.
+struct PV {
+  const float* p;
+  long long sn, sy, sx;
+  int linear;
+};
+
+__device__ __forceinline__ const float* pv_at(const PV& v, unsigned pix, unsigned hw, unsigned w, int c) {
+  if (v.linear) return v.p + (long long)pix * v.sx + c;
+  const unsigned n = pix / hw, q = pix - n * hw, y = q / w, x = q - y * w;
+  return v.p + (long long)n * v.sn + (long long)y * v.sy + (long long)x * v.sx + c;
+}
+
+static inline PV pv(const pmfb_view* v, int h, int w) {
+  PV o;
+  o.p = v ? v->ptr : nullptr;
+  o.sn = v ? v->sn : 0;
+  o.sy = v ? v->sy : 0;
+  o.sx = v ? v->sx : 0;
+  o.linear = (o.p && o.sy == (long long)w * o.sx && o.sn == (long long)h * o.sy) ? 1 : 0;
+  return o;
+}
+static inline PV pv_out(float* p, long long sn, long long sy, long long sx, int h, int w) {
+  PV o;
+  o.p = p;
+  o.sn = sn;
+  o.sy = sy;
+  o.sx = sx;
+  o.linear = (p && sy == (long long)w * sx && sn == (long long)h * sy) ? 1 : 0;
+  return o;
+}
+
+// Per-thread partial sums stay in fp32: the grid is sized so that a thread adds at most a few hundred values
+// (>= 16 pixels per thread, <= npix / (grid.x * lanes)); the cross-thread and cross-CTA reduction is fp64.
 template <int NRED>
 struct RedAcc {
   float4 f[NRED];
-  double d[NRED][4];
-  int pending;
   __device__ __forceinline__ void init() {
 #pragma unroll
-    for (int r = 0; r < NRED; ++r) {
-      f[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.0;
-    }
-    pending = 0;
-  }
-  __device__ __forceinline__ void flush() {
-#pragma unroll
-    for (int r = 0; r < NRED; ++r) {
-      d[r][0] += f[r].x; d[r][1] += f[r].y; d[r][2] += f[r].z; d[r][3] += f[r].w;
-      f[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    pending = 0;
+    for (int r = 0; r < NRED; ++r) f[r] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __device__ __forceinline__ void add(int r, float4 v) {
     f[r].x += v.x; f[r].y += v.y; f[r].z += v.z; f[r].w += v.w;
   }
-  __device__ __forceinline__ void step() {
-    if (++pending == 64) flush();
+  __device__ __forceinline__ double get(int r, int k) const {
+    return k == 0 ? (double)f[r].x : k == 1 ? (double)f[r].y : k == 2 ? (double)f[r].z : (double)f[r].w;
   }
 };
 
-// F::operator()(ni, y, x, c, acc) consumes one (pixel, 4-channel group).
+// F::load(pix, c, L&) issues the global loads of one (pixel, 4-channel group); F::consume(pix, c, L&, acc) uses them.
+// Four pixels are loaded before the first is consumed, so every thread keeps >= 4 independent 16-byte loads per
+// operand in flight (these kernels are pure HBM streams).
 template <int NRED, class F>
-__global__ void __launch_bounds__(kRedThreads)
-chan_reduce_kernel(F f, int n, int h, int w, int c4, int G, int per_image, double* __restrict__ out) {
+__global__ void __launch_bounds__(kRedThreads, 3)
+chan_reduce_kernel(F f, unsigned npix, unsigned hw, unsigned w, int c4, int G, int per_image, double* __restrict__ out) {
   __shared__ double sm[NRED * 4][kRedThreads];
   const int L = kRedThreads / G;
   const int gl = threadIdx.x % G, pl = threadIdx.x / G;
   const int cg = blockIdx.y * G + gl;
   const bool active = (pl < L) && (cg < c4);
-  const long long hw = (long long)h * w;
-  const long long npix = per_image ? hw : (long long)n * hw;
-  const int img0 = per_image ? blockIdx.z : 0;
+  const unsigned img0 = per_image ? blockIdx.z : 0;
+  const unsigned base = img0 * hw;  // per_image: npix == hw pixels of image blockIdx.z
   RedAcc<NRED> acc;
   acc.init();
   if (active) {
-    for (long long p = (long long)blockIdx.x * L + pl; p < npix; p += (long long)gridDim.x * L) {
-      const int ni = per_image ? img0 : (int)(p / hw);
-      const long long q = per_image ? p : p - (long long)ni * hw;
-      const int y = (int)(q / w), x = (int)(q % w);
-      f(ni, y, x, cg * 4, acc);
-      acc.step();
+    const unsigned stride = gridDim.x * L;
+    const int c = cg * 4;
+    unsigned p = blockIdx.x * L + pl;
+    typename F::Consts k;
+    f.prep(c, k);  // per-channel constants of this thread's four channels, loaded once
+    constexpr int U = F::kUnroll;
+    for (; p + (U - 1) * stride < npix; p += U * stride) {
+      typename F::Loaded l[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) f.load(base + p + u * stride, hw, w, c, l[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) f.consume(base + p + u * stride, hw, w, c, k, l[u], acc);
     }
-    acc.flush();
+    for (; p < npix; p += stride) {
+      typename F::Loaded l0;
+      f.load(base + p, hw, w, c, l0);
+      f.consume(base + p, hw, w, c, k, l0, acc);
+    }
   }
 #pragma unroll
   for (int r = 0; r < NRED; ++r)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) sm[r * 4 + k][threadIdx.x] = active ? acc.d[r][k] : 0.0;
+    for (int k = 0; k < 4; ++k) sm[r * 4 + k][threadIdx.x] = active ? acc.get(r, k) : 0.0;
   __syncthreads();
   if (out && pl == 0 && cg < c4) {
     const int C = c4 * 4;
@@ -86,18 +119,31 @@ chan_reduce_kernel(F f, int n, int h, int w, int c4, int G, int per_image, doubl
 }
 
 struct StatsF {
-  EpiView x;
-  __device__ __forceinline__ void operator()(int ni, int y, int xx, int c, RedAcc<2>& a) const {
-    const float4 v = ld4(x.p + (long long)ni * x.sn + (long long)y * x.sy + (long long)xx * x.sx + c);
-    a.add(0, v);
-    a.add(1, make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w));
+  static constexpr int kUnroll = 4;
+  PV x;
+  struct Loaded { float4 v; };
+  struct Consts {};
+  __device__ __forceinline__ void prep(int, Consts&) const {}
+  __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const {
+    l.v = ld4(pv_at(x, pix, hw, w, c));
+  }
+  __device__ __forceinline__ void consume(unsigned, unsigned, unsigned, int, const Consts&, const Loaded& l, RedAcc<2>& a) const {
+    a.add(0, l.v);
+    a.add(1, make_float4(l.v.x * l.v.x, l.v.y * l.v.y, l.v.z * l.v.z, l.v.w * l.v.w));
   }
 };
 
 struct ColsumF {
-  EpiView x;
-  __device__ __forceinline__ void operator()(int ni, int y, int xx, int c, RedAcc<1>& a) const {
-    a.add(0, ld4(x.p + (long long)ni * x.sn + (long long)y * x.sy + (long long)xx * x.sx + c));
+  static constexpr int kUnroll = 4;
+  PV x;
+  struct Loaded { float4 v; };
+  struct Consts {};
+  __device__ __forceinline__ void prep(int, Consts&) const {}
+  __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const {
+    l.v = ld4(pv_at(x, pix, hw, w, c));
+  }
+  __device__ __forceinline__ void consume(unsigned, unsigned, unsigned, int, const Consts&, const Loaded& l, RedAcc<1>& a) const {
+    a.add(0, l.v);
   }
 };
 
@@ -112,26 +158,35 @@ __device__ __forceinline__ float act_grad(int act, float z) {
 
 // g = dy * mul * act'(z); z is either stored (zv) or recomputed as act(alpha*x + beta) (sigmoid gate).
 struct GradIn {
-  EpiView dy, mul, z, x;
+  PV dy, mul, z, x;
   const float* mean;
   const float* invstd;
   const float* alpha;
   const float* beta;
   int act_z;
-  __device__ __forceinline__ void load(int ni, int y, int xx, int c, float4& g, float4& xhat, float4& xv) const {
-    g = ld4(dy.p + (long long)ni * dy.sn + (long long)y * dy.sy + (long long)xx * dy.sx + c);
-    if (mul.p) {
-      const float4 m = ld4(mul.p + (long long)ni * mul.sn + (long long)y * mul.sy + (long long)xx * mul.sx + c);
-      g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
-    }
-    xv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (x.p) xv = ld4(x.p + (long long)ni * x.sn + (long long)y * x.sy + (long long)xx * x.sx + c);
+  struct Loaded { float4 g, m, zz, xv; };
+  struct Consts { float4 mu, is, a, b; };
+  __device__ __forceinline__ void prep(int c, Consts& k) const {
+    k.mu = k.is = k.a = k.b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mean) { k.mu = ld4(mean + c); k.is = ld4(invstd + c); }
+    if (act_z && !z.p) { k.a = ld4(alpha + c); k.b = ld4(beta + c); }
+  }
+  __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const {
+    l.g = ld4(pv_at(dy, pix, hw, w, c));
+    if (mul.p) l.m = ld4(pv_at(mul, pix, hw, w, c));
+    if (x.p) l.xv = ld4(pv_at(x, pix, hw, w, c));
+    if (act_z && z.p) l.zz = ld4(pv_at(z, pix, hw, w, c));
+  }
+  __device__ __forceinline__ void finish(const Consts& k, const Loaded& l, float4& g, float4& xhat, float4& xv) const {
+    g = l.g;
+    if (mul.p) { g.x *= l.m.x; g.y *= l.m.y; g.z *= l.m.z; g.w *= l.m.w; }
+    xv = x.p ? l.xv : make_float4(0.f, 0.f, 0.f, 0.f);
     if (act_z) {
       float4 zz;
       if (z.p) {
-        zz = ld4(z.p + (long long)ni * z.sn + (long long)y * z.sy + (long long)xx * z.sx + c);
+        zz = l.zz;
       } else {
-        const float4 a = ld4(alpha + c), b = ld4(beta + c);
+        const float4 a = k.a, b = k.b;
         zz = make_float4(epi_act(act_z, a.x * xv.x + b.x), epi_act(act_z, a.y * xv.y + b.y),
                          epi_act(act_z, a.z * xv.z + b.z), epi_act(act_z, a.w * xv.w + b.w));
       }
@@ -139,7 +194,7 @@ struct GradIn {
       g.z *= act_grad(act_z, zz.z); g.w *= act_grad(act_z, zz.w);
     }
     if (mean) {
-      const float4 mu = ld4(mean + c), is = ld4(invstd + c);
+      const float4 mu = k.mu, is = k.is;
       xhat = make_float4((xv.x - mu.x) * is.x, (xv.y - mu.y) * is.y, (xv.z - mu.z) * is.z, (xv.w - mu.w) * is.w);
     } else {
       xhat = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -148,10 +203,15 @@ struct GradIn {
 };
 
 struct BnBwdReduceF {
+  static constexpr int kUnroll = 2;
   GradIn in;
-  __device__ __forceinline__ void operator()(int ni, int y, int xx, int c, RedAcc<2>& a) const {
+  typedef GradIn::Loaded Loaded;
+  typedef GradIn::Consts Consts;
+  __device__ __forceinline__ void prep(int c, Consts& k) const { in.prep(c, k); }
+  __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const { in.load(pix, hw, w, c, l); }
+  __device__ __forceinline__ void consume(unsigned, unsigned, unsigned, int, const Consts& k, const Loaded& l, RedAcc<2>& a) const {
     float4 g, xh, xv;
-    in.load(ni, y, xx, c, g, xh, xv);
+    in.finish(k, l, g, xh, xv);
     a.add(0, g);
     a.add(1, make_float4(g.x * xh.x, g.y * xh.y, g.z * xh.z, g.w * xh.w));
   }
@@ -160,49 +220,58 @@ struct BnBwdReduceF {
 // With BN (in.mean != NULL): dx = gamma*invstd*(g - S1/M - xhat*S2/M) [* leaky'(x)].
 // Without BN: dx = g [* leaky'(x)]   (plain activation backward, e.g. the conv->LeakyReLU shortcuts).
 struct BnBwdApplyF {
+  static constexpr int kUnroll = 2;
   GradIn in;
   const float* gamma;
   const double* red;
   double inv_count;
   int C, leaky_x, round_out;
-  float* dx;
-  long long d_sn, d_sy, d_sx;
-  float* g_out;
-  long long g_sn, g_sy, g_sx;
+  PV dx;
+  PV g_out;
   int g_accumulate;
-  __device__ __forceinline__ void operator()(int ni, int y, int xx, int c, RedAcc<1>& a) const {
+  struct Loaded { GradIn::Loaded i; float4 e; };
+  struct Consts { GradIn::Consts i; float4 gi, m1, m2; };
+  __device__ __forceinline__ void prep(int c, Consts& k) const {
+    in.prep(c, k.i);
+    k.gi = k.m1 = k.m2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in.mean) {
+      const float4 gm = ld4(gamma + c);
+      k.gi = make_float4(gm.x * k.i.is.x, gm.y * k.i.is.y, gm.z * k.i.is.z, gm.w * k.i.is.w);
+      k.m1 = make_float4((float)(red[c] * inv_count), (float)(red[c + 1] * inv_count), (float)(red[c + 2] * inv_count),
+                         (float)(red[c + 3] * inv_count));
+      k.m2 = make_float4((float)(red[C + c] * inv_count), (float)(red[C + c + 1] * inv_count),
+                         (float)(red[C + c + 2] * inv_count), (float)(red[C + c + 3] * inv_count));
+    }
+  }
+  __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const {
+    in.load(pix, hw, w, c, l.i);
+    if (g_out.p && g_accumulate) l.e = ld4(pv_at(g_out, pix, hw, w, c));
+  }
+  __device__ __forceinline__ void consume(unsigned pix, unsigned hw, unsigned w, int c, const Consts& k, const Loaded& l,
+                                          RedAcc<1>& a) const {
     float4 g, xh, xv;
-    in.load(ni, y, xx, c, g, xh, xv);
-    if (g_out) {
-      float* gp = g_out + (long long)ni * g_sn + (long long)y * g_sy + (long long)xx * g_sx + c;
+    in.finish(k.i, l.i, g, xh, xv);
+    if (g_out.p) {
       float4 o = g;
-      if (g_accumulate) {
-        const float4 e = *reinterpret_cast<const float4*>(gp);
-        o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
-      }
-      *reinterpret_cast<float4*>(gp) = o;
+      if (g_accumulate) { o.x += l.e.x; o.y += l.e.y; o.z += l.e.z; o.w += l.e.w; }
+      *reinterpret_cast<float4*>(const_cast<float*>(pv_at(g_out, pix, hw, w, c))) = o;
     }
     float4 d = g;
     if (in.mean) {
-      const float4 gm = ld4(gamma + c), is = ld4(in.invstd + c);
-      const float m1[4] = {(float)(red[c] * inv_count), (float)(red[c + 1] * inv_count), (float)(red[c + 2] * inv_count),
-                           (float)(red[c + 3] * inv_count)};
-      const float m2[4] = {(float)(red[C + c] * inv_count), (float)(red[C + c + 1] * inv_count),
-                           (float)(red[C + c + 2] * inv_count), (float)(red[C + c + 3] * inv_count)};
-      d.x = gm.x * is.x * (g.x - m1[0] - xh.x * m2[0]);
-      d.y = gm.y * is.y * (g.y - m1[1] - xh.y * m2[1]);
-      d.z = gm.z * is.z * (g.z - m1[2] - xh.z * m2[2]);
-      d.w = gm.w * is.w * (g.w - m1[3] - xh.w * m2[3]);
+      d.x = k.gi.x * (g.x - k.m1.x - xh.x * k.m2.x);
+      d.y = k.gi.y * (g.y - k.m1.y - xh.y * k.m2.y);
+      d.z = k.gi.z * (g.z - k.m1.z - xh.z * k.m2.z);
+      d.w = k.gi.w * (g.w - k.m1.w - xh.w * k.m2.w);
     }
     if (leaky_x) {
       d.x *= xv.x > 0.f ? 1.f : 0.01f; d.y *= xv.y > 0.f ? 1.f : 0.01f;
       d.z *= xv.z > 0.f ? 1.f : 0.01f; d.w *= xv.w > 0.f ? 1.f : 0.01f;
     }
+    a.add(0, d);  // bias gradient of the preceding conv: summed before the tf32 rounding of the stored value
     if (round_out) {
       d.x = round_tf32(d.x); d.y = round_tf32(d.y); d.z = round_tf32(d.z); d.w = round_tf32(d.w);
     }
-    if (dx) *reinterpret_cast<float4*>(dx + (long long)ni * d_sn + (long long)y * d_sy + (long long)xx * d_sx + c) = d;
-    a.add(0, d);
+    if (dx.p) *reinterpret_cast<float4*>(const_cast<float*>(pv_at(dx, pix, hw, w, c))) = d;
   }
 };
 
@@ -244,15 +313,6 @@ __global__ void red_to_params_kernel(const double* __restrict__ red, int c, floa
   if (dgamma) dgamma[i] = (float)red[c + i];
 }
 
-static inline EpiView ev(const pmfb_view* v) {
-  EpiView e;
-  e.p = v ? v->ptr : nullptr;
-  e.sn = v ? v->sn : 0;
-  e.sy = v ? v->sy : 0;
-  e.sx = v ? v->sx : 0;
-  return e;
-}
-
 static inline bool vok(const pmfb_view* v) {
   return !v || !v->ptr || ((((v->sn | v->sy | v->sx) % 4) == 0) && ((reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0));
 }
@@ -266,7 +326,7 @@ static inline RedGrid red_grid(long long npix, int c4, int images) {
   r.G = c4 < kRedThreads ? c4 : kRedThreads;
   const int L = kRedThreads / r.G;
   const int gy = (c4 + r.G - 1) / r.G;
-  long long gx = (npix + (long long)L * 8 - 1) / ((long long)L * 8);  // >= 8 pixels per thread
+  long long gx = (npix + (long long)L * 16 - 1) / ((long long)L * 16);  // >= 16 pixels per thread
   long long cap = (148 * 8) / ((long long)gy * images);
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
@@ -289,8 +349,9 @@ extern "C" int pmfb_bn_stats(const pmfb_view* x, int32_t n, int32_t h, int32_t w
   const long long npix = (long long)n * h * w;
   if (npix == 0) return PMFB_OK;
   RedGrid g = red_grid(npix, c / 4, 1);
-  StatsF f{ev(x)};
-  chan_reduce_kernel<2, StatsF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, n, h, w, c / 4, g.G, 0, sums);
+  StatsF f{pv(x, h, w)};
+  chan_reduce_kernel<2, StatsF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, (unsigned)npix, (unsigned)(h * w), (unsigned)w,
+                                                                                  c / 4, g.G, 0, sums);
   PMFB_LAUNCH_CHECK("bn_stats");
   return PMFB_OK;
 }
@@ -301,8 +362,9 @@ extern "C" int pmfb_colsum(const pmfb_view* x, int32_t n, int32_t h, int32_t w, 
   const long long npix = per_image ? (long long)h * w : (long long)n * h * w;
   if (npix == 0 || n == 0) return PMFB_OK;
   RedGrid g = red_grid(npix, c / 4, per_image ? n : 1);
-  ColsumF f{ev(x)};
-  chan_reduce_kernel<1, ColsumF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, n, h, w, c / 4, g.G, per_image, out);
+  ColsumF f{pv(x, h, w)};
+  chan_reduce_kernel<1, ColsumF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, (unsigned)npix, (unsigned)(h * w), (unsigned)w,
+                                                                                   c / 4, g.G, per_image, out);
   PMFB_LAUNCH_CHECK("colsum");
   return PMFB_OK;
 }
@@ -320,17 +382,18 @@ extern "C" int pmfb_bn_finalize(const double* sums, int64_t count, int32_t c, co
 }
 
 static int fill_grad_in(GradIn* gi, const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int act_z,
-                        const pmfb_view* x, const float* mean, const float* invstd, const float* alpha, const float* beta) {
+                        const pmfb_view* x, const float* mean, const float* invstd, const float* alpha, const float* beta,
+                        int h, int w) {
   if (!dy || !dy->ptr || !vok(dy) || !vok(mul) || !vok(z) || !vok(x)) return fail(PMFB_ERR_INVALID, "bn_bwd: bad views");
   if (act_z < 0 || act_z > 3) return fail(PMFB_ERR_INVALID, "bn_bwd: act_z=%d", act_z);
   if (act_z && !(z && z->ptr) && !(alpha && beta && x && x->ptr))
     return fail(PMFB_ERR_INVALID, "bn_bwd: act_z without z needs x, alpha and beta to recompute it");
   if ((mean != nullptr) != (invstd != nullptr)) return fail(PMFB_ERR_INVALID, "bn_bwd: mean and invstd go together");
   if (mean && !(x && x->ptr)) return fail(PMFB_ERR_INVALID, "bn_bwd: BN backward needs x");
-  gi->dy = ev(dy);
-  gi->mul = ev(mul);
-  gi->z = ev(z);
-  gi->x = ev(x);
+  gi->dy = pv(dy, h, w);
+  gi->mul = pv(mul, h, w);
+  gi->z = pv(z, h, w);
+  gi->x = pv(x, h, w);
   gi->mean = mean;
   gi->invstd = invstd;
   gi->alpha = alpha;
@@ -345,12 +408,13 @@ extern "C" int pmfb_bn_bwd_reduce(const pmfb_view* dy, const pmfb_view* mul, con
                                   void* stream) {
   REQ(red && mean && c > 0 && c % 4 == 0, "bn_bwd_reduce: bad arguments");
   BnBwdReduceF f;
-  int rc = fill_grad_in(&f.in, dy, mul, z, act_z, x, mean, invstd, alpha, beta);
+  int rc = fill_grad_in(&f.in, dy, mul, z, act_z, x, mean, invstd, alpha, beta, h, w);
   if (rc) return rc;
   const long long npix = (long long)n * h * w;
   if (npix == 0) return PMFB_OK;
   RedGrid g = red_grid(npix, c / 4, 1);
-  chan_reduce_kernel<2, BnBwdReduceF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, n, h, w, c / 4, g.G, 0, red);
+  chan_reduce_kernel<2, BnBwdReduceF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, (unsigned)npix, (unsigned)(h * w),
+                                                                                        (unsigned)w, c / 4, g.G, 0, red);
   PMFB_LAUNCH_CHECK("bn_bwd_reduce");
   return PMFB_OK;
 }
@@ -368,7 +432,7 @@ extern "C" int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, cons
   REQ(!g_out || ((((g_sn | g_sy | g_sx) % 4) == 0) && ((reinterpret_cast<uintptr_t>(g_out) & 15) == 0)),
       "bn_bwd_apply: bad g_out view");
   BnBwdApplyF f;
-  int rc = fill_grad_in(&f.in, dy, mul, z, act_z, x, mean, invstd, alpha, beta);
+  int rc = fill_grad_in(&f.in, dy, mul, z, act_z, x, mean, invstd, alpha, beta, h, w);
   if (rc) return rc;
   const long long npix = (long long)n * h * w;
   if (npix == 0) return PMFB_OK;
@@ -378,13 +442,12 @@ extern "C" int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, cons
   f.C = c;
   f.leaky_x = leaky_x;
   f.round_out = round_out;
-  f.dx = dx;
-  f.d_sn = d_sn; f.d_sy = d_sy; f.d_sx = d_sx;
-  f.g_out = g_out;
-  f.g_sn = g_sn; f.g_sy = g_sy; f.g_sx = g_sx;
+  f.dx = pv_out(dx, d_sn, d_sy, d_sx, h, w);
+  f.g_out = pv_out(g_out, g_sn, g_sy, g_sx, h, w);
   f.g_accumulate = g_accumulate;
   RedGrid g = red_grid(npix, c / 4, 1);
-  chan_reduce_kernel<1, BnBwdApplyF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, n, h, w, c / 4, g.G, 0, colsum);
+  chan_reduce_kernel<1, BnBwdApplyF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, (unsigned)npix, (unsigned)(h * w),
+                                                                                       (unsigned)w, c / 4, g.G, 0, colsum);
   PMFB_LAUNCH_CHECK("bn_bwd_apply");
   if (mean && (dgamma || dbeta)) {
     red_to_params_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(red, c, dgamma, dbeta);

@@ -32,23 +32,65 @@ __device__ __forceinline__ float4 rnd4(float4 v) {
 }
 
 // ------------------------------------------------------------------------------------ pointwise
+// Thread = (fixed 4-channel group, pixel lane); four pixels per trip with every operand load issued before the first
+// use.  Pixel-linear views (offset = pixel * sx) avoid all index divisions; broadcast / parity views decode.
+struct PWV {
+  const float* p;
+  long long sn, sy, sx;
+  int linear;
+};
+__device__ __forceinline__ const float* pw_at(const PWV& v, unsigned pix, unsigned hw, unsigned w, int c) {
+  if (v.linear) return v.p + (long long)pix * v.sx + c;
+  const unsigned n = pix / hw, q = pix - n * hw, y = q / w, x = q - y * w;
+  return v.p + (long long)n * v.sn + (long long)y * v.sy + (long long)x * v.sx + c;
+}
+struct PWParams {
+  PWV in, out, r1, mul, r2;
+  const float* alpha1;
+  const float* beta1;
+  const float* alpha2;
+  const float* beta2;
+  int act, round_out;
+};
+
 __global__ void __launch_bounds__(256)
-pointwise_kernel(EpiView in, float* out, long long o_sn, long long o_sy, long long o_sx, int n, int h, int w, int c4,
-                 EpiParams E) {
-  const long long total = (long long)n * h * w * c4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c4);
-    long long p = i / c4;
-    const int x = (int)(p % w);
-    p /= w;
-    const int y = (int)(p % h);
-    const int ni = (int)(p / h);
-    const int c = cg * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (in.p) v = ld4(in.p + (long long)ni * in.sn + (long long)y * in.sy + (long long)x * in.sx + c);
-    EpiPixel ep = epi_pixel(E, ni, y, x);
-    v = epi_apply4(E, ep, c, v);
-    *reinterpret_cast<float4*>(out + (long long)ni * o_sn + (long long)y * o_sy + (long long)x * o_sx + c) = v;
+pointwise_kernel(PWParams P, unsigned npix, unsigned hw, unsigned w, int c4, int G) {
+  const int L = 256 / G;
+  const int gl = threadIdx.x % G, pl = threadIdx.x / G;
+  const int cg = blockIdx.y * G + gl;
+  if (pl >= L || cg >= c4) return;
+  const int c = cg * 4;
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 a1 = P.alpha1 ? ld4(P.alpha1 + c) : one, b1 = P.beta1 ? ld4(P.beta1 + c) : zero;
+  const float4 a2 = P.alpha2 ? ld4(P.alpha2 + c) : one, b2 = P.beta2 ? ld4(P.beta2 + c) : zero;
+  const unsigned stride = gridDim.x * L;
+  for (unsigned p0 = blockIdx.x * L + pl; p0 < npix; p0 += 4 * stride) {
+    float4 v[4], r1[4], mu[4], r2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned p = p0 + k * stride;
+      if (p < npix) {
+        v[k] = P.in.p ? ld4(pw_at(P.in, p, hw, w, c)) : zero;
+        if (P.r1.p) r1[k] = ld4(pw_at(P.r1, p, hw, w, c));
+        if (P.mul.p) mu[k] = ld4(pw_at(P.mul, p, hw, w, c));
+        if (P.r2.p) r2[k] = ld4(pw_at(P.r2, p, hw, w, c));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned p = p0 + k * stride;
+      if (p < npix) {
+        float4 o = v[k];
+        o.x = o.x * a1.x + b1.x; o.y = o.y * a1.y + b1.y; o.z = o.z * a1.z + b1.z; o.w = o.w * a1.w + b1.w;
+        if (P.r1.p) { o.x += r1[k].x; o.y += r1[k].y; o.z += r1[k].z; o.w += r1[k].w; }
+        if (P.act) { o.x = epi_act(P.act, o.x); o.y = epi_act(P.act, o.y); o.z = epi_act(P.act, o.z); o.w = epi_act(P.act, o.w); }
+        o.x = o.x * a2.x + b2.x; o.y = o.y * a2.y + b2.y; o.z = o.z * a2.z + b2.z; o.w = o.w * a2.w + b2.w;
+        if (P.mul.p) { o.x *= mu[k].x; o.y *= mu[k].y; o.z *= mu[k].z; o.w *= mu[k].w; }
+        if (P.r2.p) { o.x += r2[k].x; o.y += r2[k].y; o.z += r2[k].z; o.w += r2[k].w; }
+        if (P.round_out) o = rnd4(o);
+        *reinterpret_cast<float4*>(const_cast<float*>(pw_at(P.out, p, hw, w, c))) = o;
+      }
+    }
   }
 }
 
@@ -532,6 +574,16 @@ extern "C" int pmfb_memset_zero(void* ptr, size_t bytes, void* stream) {
   return PMFB_OK;
 }
 
+static inline PWV pwv(const float* p, long long sn, long long sy, long long sx, int h, int w) {
+  PWV o;
+  o.p = p;
+  o.sn = sn;
+  o.sy = sy;
+  o.sx = sx;
+  o.linear = (p && sy == (long long)w * sx && sn == (long long)h * sy) ? 1 : 0;
+  return o;
+}
+
 extern "C" int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n,
                               int32_t h, int32_t w, int32_t c, const pmfb_epilogue* epi, void* stream) {
   REQ(epi && c > 0 && c % 4 == 0, "pointwise: c=%d must be a positive multiple of 4", c);
@@ -540,9 +592,32 @@ extern "C" int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int
   EpiParams E;
   int rc = epi_from_c(epi, &E);
   if (rc) return rc;
-  const long long total = (long long)n * h * w * (c / 4);
-  if (total == 0) return PMFB_OK;
-  pointwise_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(in), out, o_sn, o_sy, o_sx, n, h, w, c / 4, E);
+  const long long npix = (long long)n * h * w;
+  if (npix == 0) return PMFB_OK;
+  REQ(npix < (1ll << 31), "pointwise: too many pixels");
+  PWParams P;
+  P.in = in ? pwv(in->ptr, in->sn, in->sy, in->sx, h, w) : pwv(nullptr, 0, 0, 0, h, w);
+  P.out = pwv(out, o_sn, o_sy, o_sx, h, w);
+  P.r1 = pwv(E.r1.p, E.r1.sn, E.r1.sy, E.r1.sx, h, w);
+  P.mul = pwv(E.mul.p, E.mul.sn, E.mul.sy, E.mul.sx, h, w);
+  P.r2 = pwv(E.r2.p, E.r2.sn, E.r2.sy, E.r2.sx, h, w);
+  P.alpha1 = E.alpha1;
+  P.beta1 = E.beta1;
+  P.alpha2 = E.alpha2;
+  P.beta2 = E.beta2;
+  P.act = E.act;
+  P.round_out = E.round_out;
+  const int c4 = c / 4;
+  const int G = c4 < 256 ? c4 : 256;
+  const int L = 256 / G;
+  const int gy = (c4 + G - 1) / G;
+  long long gx = (npix + (long long)L * 8 - 1) / ((long long)L * 8);
+  long long cap = (148 * 16) / gy;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  pointwise_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(P, (unsigned)npix, (unsigned)(h * w),
+                                                                                     (unsigned)w, c4, G);
   PMFB_LAUNCH_CHECK("pointwise_kernel");
   return PMFB_OK;
 }
