@@ -1,0 +1,2 @@
+"""pc_processor.models — the names the reference exports (pc_processor/models/__init__.py:1-3) that are on the hot path."""
+from .pmf_net import PMFNet  # noqa: F401

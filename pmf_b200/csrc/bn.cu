@@ -321,13 +321,22 @@ struct RedGrid {
   dim3 grid;
   int G;
 };
-static inline RedGrid red_grid(long long npix, int c4, int images) {
+// One resident wave: grid.x * grid.y * grid.z == SMs * (blocks of this kernel an SM can hold), so no tail wave.
+template <class K>
+static inline RedGrid red_grid(K kernel, long long npix, int c4, int images) {
+  static int per_sm = 0, sms = 0;  // one static pair per kernel instantiation
+  if (per_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRedThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  }
   RedGrid r;
   r.G = c4 < kRedThreads ? c4 : kRedThreads;
   const int L = kRedThreads / r.G;
   const int gy = (c4 + r.G - 1) / r.G;
   long long gx = (npix + (long long)L * 16 - 1) / ((long long)L * 16);  // >= 16 pixels per thread
-  long long cap = (148 * 8) / ((long long)gy * images);
+  long long cap = ((long long)sms * per_sm) / ((long long)gy * images);
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
@@ -348,7 +357,7 @@ extern "C" int pmfb_bn_stats(const pmfb_view* x, int32_t n, int32_t h, int32_t w
   REQ(x && x->ptr && vok(x) && sums && c > 0 && c % 4 == 0, "bn_stats: bad arguments (c=%d)", c);
   const long long npix = (long long)n * h * w;
   if (npix == 0) return PMFB_OK;
-  RedGrid g = red_grid(npix, c / 4, 1);
+  RedGrid g = red_grid(chan_reduce_kernel<2, StatsF>, npix, c / 4, 1);
   StatsF f{pv(x, h, w)};
   chan_reduce_kernel<2, StatsF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, (unsigned)npix, (unsigned)(h * w), (unsigned)w,
                                                                                   c / 4, g.G, 0, sums);
@@ -361,7 +370,7 @@ extern "C" int pmfb_colsum(const pmfb_view* x, int32_t n, int32_t h, int32_t w, 
   REQ(x && x->ptr && vok(x) && out && c > 0 && c % 4 == 0, "colsum: bad arguments (c=%d)", c);
   const long long npix = per_image ? (long long)h * w : (long long)n * h * w;
   if (npix == 0 || n == 0) return PMFB_OK;
-  RedGrid g = red_grid(npix, c / 4, per_image ? n : 1);
+  RedGrid g = red_grid(chan_reduce_kernel<1, ColsumF>, npix, c / 4, per_image ? n : 1);
   ColsumF f{pv(x, h, w)};
   chan_reduce_kernel<1, ColsumF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, (unsigned)npix, (unsigned)(h * w), (unsigned)w,
                                                                                    c / 4, g.G, per_image, out);
@@ -412,7 +421,7 @@ extern "C" int pmfb_bn_bwd_reduce(const pmfb_view* dy, const pmfb_view* mul, con
   if (rc) return rc;
   const long long npix = (long long)n * h * w;
   if (npix == 0) return PMFB_OK;
-  RedGrid g = red_grid(npix, c / 4, 1);
+  RedGrid g = red_grid(chan_reduce_kernel<2, BnBwdReduceF>, npix, c / 4, 1);
   chan_reduce_kernel<2, BnBwdReduceF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, (unsigned)npix, (unsigned)(h * w),
                                                                                         (unsigned)w, c / 4, g.G, 0, red);
   PMFB_LAUNCH_CHECK("bn_bwd_reduce");
@@ -445,7 +454,7 @@ extern "C" int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, cons
   f.dx = pv_out(dx, d_sn, d_sy, d_sx, h, w);
   f.g_out = pv_out(g_out, g_sn, g_sy, g_sx, h, w);
   f.g_accumulate = g_accumulate;
-  RedGrid g = red_grid(npix, c / 4, 1);
+  RedGrid g = red_grid(chan_reduce_kernel<1, BnBwdApplyF>, npix, c / 4, 1);
   chan_reduce_kernel<1, BnBwdApplyF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, (unsigned)npix, (unsigned)(h * w),
                                                                                        (unsigned)w, c / 4, g.G, 0, colsum);
   PMFB_LAUNCH_CHECK("bn_bwd_apply");

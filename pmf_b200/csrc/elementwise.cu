@@ -611,8 +611,11 @@ extern "C" int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int
   const int G = c4 < 256 ? c4 : 256;
   const int L = 256 / G;
   const int gy = (c4 + G - 1) / G;
+  static int per_sm = 0;
+  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pointwise_kernel, 256, 0) != cudaSuccess || per_sm < 1))
+    per_sm = 4;
   long long gx = (npix + (long long)L * 8 - 1) / ((long long)L * 8);
-  long long cap = (148 * 16) / gy;
+  long long cap = (148ll * per_sm) / gy;  // one resident wave
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
