@@ -71,7 +71,7 @@ struct RedAcc {
 template <int NRED, class F>
 __global__ void __launch_bounds__(kRedThreads, 3)
 chan_reduce_kernel(F f, unsigned npix, unsigned hw, unsigned w, int c4, int G, int per_image, double* __restrict__ out) {
-  __shared__ double sm[NRED * 4][kRedThreads];
+  __shared__ float sm[NRED * 4 * kRedThreads];
   const int L = kRedThreads / G;
   const int gl = threadIdx.x % G, pl = threadIdx.x / G;
   const int cg = blockIdx.y * G + gl;
@@ -100,21 +100,27 @@ chan_reduce_kernel(F f, unsigned npix, unsigned hw, unsigned w, int c4, int G, i
       f.consume(base + p, hw, w, c, k, l0, acc);
     }
   }
+  // Block reduction: every thread parks its NRED*4 fp32 partials in shared memory; G*NRED*4 threads then each sum one
+  // (channel, quantity) over the L pixel lanes in fp64 and issue ONE atomic.  A block owns at most 32 channels (G <= 8),
+  // so a launch issues (pixel blocks) x C x NRED atomics in total instead of (all blocks) x C x NRED: ncu showed the
+  // atomic drain, not the streaming loop, dominating the small-tensor launches.
 #pragma unroll
-  for (int r = 0; r < NRED; ++r)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) sm[r * 4 + k][threadIdx.x] = active ? acc.get(r, k) : 0.0;
+  for (int r = 0; r < NRED; ++r) {
+    sm[(r * 4 + 0) * kRedThreads + threadIdx.x] = active ? acc.f[r].x : 0.f;
+    sm[(r * 4 + 1) * kRedThreads + threadIdx.x] = active ? acc.f[r].y : 0.f;
+    sm[(r * 4 + 2) * kRedThreads + threadIdx.x] = active ? acc.f[r].z : 0.f;
+    sm[(r * 4 + 3) * kRedThreads + threadIdx.x] = active ? acc.f[r].w : 0.f;
+  }
   __syncthreads();
-  if (out && pl == 0 && cg < c4) {
-    const int C = c4 * 4;
-#pragma unroll
-    for (int r = 0; r < NRED; ++r)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        double s = 0.0;
-        for (int l = 0; l < L; ++l) s += sm[r * 4 + k][l * G + gl];
-        atomicAdd(out + ((long long)img0 * NRED + r) * C + cg * 4 + k, s);
-      }
+  if (out && (int)threadIdx.x < G * NRED * 4) {
+    const int g2 = threadIdx.x % G, q = threadIdx.x / G;  // q = r*4 + k
+    const int cg2 = blockIdx.y * G + g2;
+    if (cg2 < c4) {
+      double s = 0.0;
+      for (int l = 0; l < L; ++l) s += (double)sm[q * kRedThreads + l * G + g2];
+      const int C = c4 * 4;
+      atomicAdd(out + ((long long)img0 * NRED + (q >> 2)) * C + cg2 * 4 + (q & 3), s);
+    }
   }
 }
 
@@ -332,7 +338,7 @@ static inline RedGrid red_grid(K kernel, long long npix, int c4, int images) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRedThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
   }
   RedGrid r;
-  r.G = c4 < kRedThreads ? c4 : kRedThreads;
+  r.G = c4 < 8 ? c4 : 8;  // <= 32 channels per block: see the block-reduction note in chan_reduce_kernel
   const int L = kRedThreads / r.G;
   const int gy = (c4 + r.G - 1) / r.G;
   long long gx = (npix + (long long)L * 16 - 1) / ((long long)L * 16);  // >= 16 pixels per thread

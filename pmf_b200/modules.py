@@ -303,7 +303,7 @@ class _GraphedPMF:
         self.pcd = self.E_in.new(n, h, w, (c_pcd + 3) // 4 * 4, needs_grad=False)
         self._stage_inputs(pcd, img)
         torch.cuda.synchronize(self.dev)
-        with torch.cuda.graph(self.g_fwd, pool=self.pool):
+        with torch.cuda.graph(self.g_fwd, pool=self.pool, capture_error_mode="thread_local"):  # NCCL watchdog threads may poll events
             E = Engine(G.ModuleParams(mod), self.dev, mod.training, record, self.cache, dropout=mod._dropout_masks())
             self.lidar, self.camera, self.ll, self.cl = G.pmf_forward_packed(E, self.pcd, self.img7, mod.image_backbone,
                                                                              mod.nclasses)
@@ -339,7 +339,7 @@ class _GraphedPMF:
         E.softmax_backward_into(self.cl_grad, self.camera, d_camera, stream=st)
         if not self.bwd_captured:
             torch.cuda.synchronize(self.dev)
-            with torch.cuda.graph(self.g_bwd, pool=self.pool):
+            with torch.cuda.graph(self.g_bwd, pool=self.pool, capture_error_mode="thread_local"):
                 self.grads = E.run_backward()
             self.bwd_captured = True
         self.g_bwd.replay()
