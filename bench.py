@@ -302,6 +302,54 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
     recs = []
     orig = L.call
 
+    def vbytes(v, n, h, w, c):
+        """Algorithmic bytes of one NHWC view operand (0 for NULL / broadcast views)."""
+        v = getattr(v, "_obj", v)
+        if v is None or not getattr(v, "ptr", None) or v.sx == 0:
+            return 0.0
+        return 4.0 * n * h * w * c
+
+    def call_bytes(name, a):
+        """ALGORITHMIC HBM bytes of one C-ABI call: every full-size operand read once, every result written once
+        (DESIGN.md §3 per-kernel figures)."""
+        if name == "pmfb_pointwise":
+            n, h, w, c = a[5:9]
+            e = a[9]._obj
+            return vbytes(a[0], n, h, w, c) + 4.0 * n * h * w * c + sum(vbytes(v, n, h, w, c) for v in (e.r1, e.mul, e.r2))
+        if name == "pmfb_bn_stats":
+            return vbytes(a[0], *a[1:5])
+        if name == "pmfb_bn_bwd_reduce":
+            n, h, w, c = a[9:13]
+            return sum(vbytes(v, n, h, w, c) for v in (a[0], a[1], a[2], a[4]))
+        if name == "pmfb_bn_bwd_apply":
+            n, h, w, c = a[12:16]
+            b = sum(vbytes(v, n, h, w, c) for v in (a[0], a[1], a[2], a[4]))
+            if a[16]:
+                b += 4.0 * n * h * w * c
+            if a[24]:
+                b += 4.0 * n * h * w * c * (2 if a[28] else 1)
+            return b
+        if name == "pmfb_conv_fwd":
+            d = a[0]._obj
+            px = d.n_batch * d.out_h * d.out_w
+            in_elems = 1.0
+            for k in range(5):
+                in_elems *= d.x.dims[k]
+            return 4.0 * (in_elems + px * d.c_out * (1 + sum(1 for v in (d.epi.r1, d.epi.mul, d.epi.r2) if v.ptr and v.sx)))
+        if name == "pmfb_conv_wgrad":
+            d = a[0]._obj
+            in_elems = 1.0
+            for k in range(5):
+                in_elems *= d.x.dims[k]
+            return 4.0 * (in_elems + d.n_batch * d.out_h * d.out_w * d.c_out)
+        if name in ("pmfb_pool3s2", "pmfb_pool3s2_bwd"):
+            n, h, w, c = a[2:6]
+            return 4.0 * n * h * w * c * 1.25 + (n * h * w * c / 4.0 if a[11] else 0.0)
+        if name in ("pmfb_softmax_nchw", "pmfb_softmax_nchw_bwd"):
+            n, h, w, c = (a[1:5] if name == "pmfb_softmax_nchw" else a[2:6])
+            return 4.0 * n * h * w * c * (2 if name == "pmfb_softmax_nchw" else 3)
+        return 0.0
+
     def call(name, *a):
         flops = 0.0
         if name in ("pmfb_conv_fwd", "pmfb_conv_wgrad"):
@@ -313,7 +361,7 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
         e0.record()
         orig(name, *a)
         e1.record()
-        recs.append((name, flops, e0, e1))
+        recs.append((name, flops, e0, e1, call_bytes(name, a)))
         if flops:
             shapes.append("%s n%d %dx%d cin%d cout%d taps%d" % (name[5:], d.n_batch, d.out_h, d.out_w, d.c_in, d.c_out, d.n_taps))
         else:
@@ -338,14 +386,17 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
         else:
             os.environ["PMFB_CUDA_GRAPH"] = prev
     by = {}
-    for (n, f, e0, e1) in recs:
-        r = by.setdefault(n, [0, 0.0, 0.0])
+    for (n, f, e0, e1, nb) in recs:
+        r = by.setdefault(n, [0, 0.0, 0.0, 0.0])
         r[0] += 1
         r[1] += e0.elapsed_time(e1)
         r[2] += f
-    breakdown = {n.replace("pmfb_", ""): {"launches": r[0], "ms": round(r[1], 3)} for n, r in sorted(by.items(), key=lambda kv: -kv[1][1])}
+        r[3] += nb
+    breakdown = {n.replace("pmfb_", ""): {"launches": r[0], "ms": round(r[1], 3), "alg_gb": round(r[3] / 1e9, 3),
+                                          "alg_gbs": round(r[3] / 1e9 / max(r[1] * 1e-3, 1e-12), 1)}
+                 for n, r in sorted(by.items(), key=lambda kv: -kv[1][1])}
     in_kernels = sum(r[1] for r in by.values())
-    convs = sorted(((e0.elapsed_time(e1), f, sh) for (n, f, e0, e1), sh in zip(recs, shapes) if sh), reverse=True)
+    convs = sorted(((e0.elapsed_time(e1), f, sh) for (n, f, e0, e1, _nb), sh in zip(recs, shapes) if sh), reverse=True)
     top = [{"ms": round(t, 3), "tflops": round(f / (t * 1e-3) / 1e12, 1), "launch": sh} for t, f, sh in convs[:24]]
     if os.environ.get("PMFB_BENCH_DUMP"):
         with open(os.environ["PMFB_BENCH_DUMP"], "w") as fdump:
@@ -354,7 +405,7 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
     out = {}
     for kind in ("pmfb_conv_fwd", "pmfb_conv_wgrad"):
         if kind in by:
-            c, t, fl = by[kind]
+            c, t, fl, _nb = by[kind]
             out[kind] = {"launches": c, "gflop": fl / 1e9, "ms": t, "tflops": fl / (t * 1e-3) / 1e12}
     dom = out.get("pmfb_conv_fwd")
     if not dom:

@@ -51,6 +51,15 @@ __device__ __forceinline__ uint64_t desc_with_base(uint32_t saddr, uint32_t lbo,
   return d;
 }
 
+// EPI selects the epilogue at compile time.  kEpiGeneric evaluates the whole pmfb_epilogue functional from runtime
+// flags (eval-mode fusions: BN affine, residual, gate).  The fast variants cover what a TRAINING step launches --
+// [+bias] [LeakyReLU] [tf32 round] and [+= r1 (gradient accumulation)] [tf32 round] -- with everything else compiled
+// out: ncu showed the generic epilogue executing ~1350 warp instructions per 32x32 unit (8 warps per SM, issue and
+// dependency bound at 1.4 TB/s of stores) and every thin full-resolution layer pinned to that rate.
+constexpr int kEpiGeneric = -1;
+constexpr int kEpiB1 = 1, kEpiR1 = 2, kEpiRnd = 4, kEpiLeaky = 8;
+
+template <int EPI>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
                      const __grid_constant__ HaloK P) {
@@ -200,6 +209,51 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
       tc_fence_after();
       const int row = q * 32 + lane;
       const int units = P.mt * chunks;
+      if constexpr (EPI != kEpiGeneric) {
+        for (int u = half; u < units; u += 2) {
+          const int j = u / chunks, ch = u - j * chunks;
+          const int y = y0 + 16 * j + (row >> 3), x = x0 + (row & 7);
+          const bool valid = (y < P.out_h) && (x < P.out_w);
+          const int c0 = n0 + ch * 32;
+          const int ncol = min(32, P.n_tile - ch * 32);
+          const int nq = min(ncol, P.c_out - c0) >> 2;  // float4 groups of this unit (warp-uniform)
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(P.mt * P.n_tile) +
+                                 (uint32_t)(j * P.n_tile + ch * 32);
+          float v[32];
+          tmem_ld16(taddr, v);
+          if (ncol > 16) tmem_ld16(taddr + 16, v + 16);
+          float* optr = P.out + ((long long)n_img * P.o_sn + (long long)y * P.o_sy + (long long)x * P.o_sx) + c0;
+          float4 r1v[8];
+          if constexpr ((EPI & kEpiR1) != 0) {
+            const float* r1p = P.epi.r1.p + ((long long)n_img * P.epi.r1.sn + (long long)y * P.epi.r1.sy + (long long)x * P.epi.r1.sx) + c0;
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < nq) r1v[i] = ld4(r1p + 4 * i);
+            }
+          }
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i < nq) {
+                float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                if constexpr ((EPI & kEpiB1) != 0) {
+                  const float4 b = *reinterpret_cast<const float4*>(sv + kHMaxC + c0 + 4 * i);
+                  o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
+                if constexpr ((EPI & kEpiR1) != 0) { o.x += r1v[i].x; o.y += r1v[i].y; o.z += r1v[i].z; o.w += r1v[i].w; }
+                if constexpr ((EPI & kEpiLeaky) != 0) {
+                  o.x = fmaxf(o.x, 0.01f * o.x); o.y = fmaxf(o.y, 0.01f * o.y);
+                  o.z = fmaxf(o.z, 0.01f * o.z); o.w = fmaxf(o.w, 0.01f * o.w);
+                }
+                if constexpr ((EPI & kEpiRnd) != 0) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                *reinterpret_cast<float4*>(optr + 4 * i) = o;
+              }
+            }
+          }
+        }
+      } else
       for (int u = half; u < units; u += 2) {
         const int j = u / chunks, ch = u - j * chunks;
         const int y = y0 + 16 * j + (row >> 3), x = x0 + (row & 7);
@@ -274,6 +328,29 @@ int halo_eligible(const pmfb_conv_desc* d) {
     if (ay > hy) hy = ay;
   }
   return (hx <= 2 && hy <= 3 && d->c_out <= kHMaxC) ? 1 : 0;
+}
+
+template <int EPI>
+static int launch_halo_t(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& tmx, const CUtensorMap& tmw, const HaloK& P) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PMFB_CUDA_CHECK(cudaFuncSetAttribute(conv_fwd_halo_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemBudget + 2048));
+    attr_set = true;
+  }
+  conv_fwd_halo_kernel<EPI><<<grid, kHThreads, smem, stream>>>(tmx, tmw, P);
+  PMFB_LAUNCH_CHECK("conv_fwd_halo_kernel");
+  return PMFB_OK;
+}
+
+static int launch_halo_variant(int epi, int grid, size_t smem, cudaStream_t stream, const CUtensorMap& tmx, const CUtensorMap& tmw,
+                               const HaloK& P) {
+  switch (epi) {
+#define PMFB_HV(e) case e: return launch_halo_t<e>(grid, smem, stream, tmx, tmw, P);
+    PMFB_HV(0) PMFB_HV(1) PMFB_HV(2) PMFB_HV(3) PMFB_HV(4) PMFB_HV(5) PMFB_HV(6) PMFB_HV(7)
+    PMFB_HV(8) PMFB_HV(9) PMFB_HV(12) PMFB_HV(13)
+#undef PMFB_HV
+    default: return launch_halo_t<kEpiGeneric>(grid, smem, stream, tmx, tmw, P);
+  }
 }
 
 int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
@@ -377,16 +454,21 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   if (rc) return rc;
 
   const size_t smem = (size_t)kHCtrlBytes + 2 * (size_t)P.a_bytes + (size_t)nsb * b_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PMFB_CUDA_CHECK(cudaFuncSetAttribute(conv_fwd_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemBudget + 2048));
-    attr_set = true;
-  }
   const long long total = (long long)P.tiles_x * P.tiles_y * P.n_batch * P.n_blocks;
   const int grid = (int)(total < sm_count ? total : sm_count);
-  conv_fwd_halo_kernel<<<grid, kHThreads, smem, (cudaStream_t)stream>>>(tmx, tmw, P);
-  PMFB_LAUNCH_CHECK("conv_fwd_halo_kernel");
-  return PMFB_OK;
+  // epilogue variant
+  int epi = kEpiGeneric;
+  static int fast_mode = -1;
+  if (fast_mode < 0) {
+    const char* e = getenv("PMFB_HALO_FAST_EPI");
+    fast_mode = e ? atoi(e) : 1;
+  }
+  const pmfb_epilogue& E = d->epi;
+  if (fast_mode && !E.alpha1 && !E.alpha2 && !E.beta2 && !E.mul.ptr && !E.r2.ptr &&
+      (E.act == PMFB_ACT_NONE || E.act == PMFB_ACT_LEAKY) && !(E.r1.ptr && E.act != PMFB_ACT_NONE)) {
+    epi = (E.beta1 ? kEpiB1 : 0) | (E.r1.ptr ? kEpiR1 : 0) | (E.round_out ? kEpiRnd : 0) | (E.act == PMFB_ACT_LEAKY ? kEpiLeaky : 0);
+  }
+  return launch_halo_variant(epi, grid, smem, (cudaStream_t)stream, tmx, tmw, P);
 }
 
 }  // namespace pmfb

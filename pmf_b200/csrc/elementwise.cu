@@ -267,53 +267,60 @@ pool3s2_kernel(int kind, EpiView xin, int n, int h, int w, int c4, const float* 
   }
 }
 
-// gather form: every input pixel sums the (at most 4) output windows that cover it.
+// gather form: every input pixel sums the (at most 4) output windows that cover it.  32-bit index arithmetic and all
+// four candidate loads (plus the accumulate read) issued before the first use: the kernel is a pure HBM stream.
 __global__ void __launch_bounds__(256)
 pool3s2_bwd_kernel(int kind, EpiView dy, int n, int h, int w, int c4, const float* __restrict__ chan_scale, float* dx,
                    long long d_sn, long long d_sy, long long d_sx, const uint8_t* __restrict__ idx, int accumulate) {
-  const int ho = h / 2, wo = w / 2;
-  const long long total = (long long)n * h * w * c4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c4);
-    long long p = i / c4;
-    const int x = (int)(p % w);
-    p /= w;
-    const int y = (int)(p % h);
-    const int ni = (int)(p / h);
+  const unsigned ho = h / 2, wo = w / 2;
+  const unsigned total = (unsigned)n * h * w * c4;  // host guarantees < 2^32
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned cg = i % (unsigned)c4;
+    unsigned p = i / (unsigned)c4;
+    const unsigned x = p % (unsigned)w;
+    p /= (unsigned)w;
+    const unsigned y = p % (unsigned)h;
+    const unsigned ni = p / (unsigned)h;
     const int c = cg * 4;
+    // windows: 2*yo-1 <= y <= 2*yo+1  ->  yo in {y/2, (y+1)/2}
+    const unsigned yo[2] = {y / 2, (y + 1) / 2}, xo[2] = {x / 2, (x + 1) / 2};
+    const bool vy[2] = {true, (y & 1u) && yo[1] < ho}, vx[2] = {true, (x & 1u) && xo[1] < wo};
+    float4 g[4];
+    uchar4 am[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int a = k >> 1, b = k & 1;
+      g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      am[k] = make_uchar4(255, 255, 255, 255);
+      if (vy[a] && vx[b]) {
+        g[k] = ld4(dy.p + (long long)ni * dy.sn + (long long)yo[a] * dy.sy + (long long)xo[b] * dy.sx + c);
+        if (kind != 0)
+          am[k] = *reinterpret_cast<const uchar4*>(idx + (((long long)ni * ho + yo[a]) * wo + xo[b]) * (c4 * 4) + c);
+      }
+    }
+    float* d = dx + (long long)ni * d_sn + (long long)y * d_sy + (long long)x * d_sx + c;
+    float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (accumulate) old = *reinterpret_cast<const float4*>(d);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (chan_scale) sc = ld4(chan_scale + (long long)ni * (c4 * 4) + c);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    // windows: 2*yo-1 <= y <= 2*yo+1  ->  yo in [ceil((y-1)/2), floor((y+1)/2)]
-    const int yo_lo = y / 2, yo_hi = (y + 1) / 2;
-    const int xo_lo = x / 2, xo_hi = (x + 1) / 2;
-    for (int yo = yo_lo; yo <= yo_hi; ++yo) {
-      if (yo >= ho) continue;
-      for (int xo = xo_lo; xo <= xo_hi; ++xo) {
-        if (xo >= wo) continue;
-        const float4 g = ld4(dy.p + (long long)ni * dy.sn + (long long)yo * dy.sy + (long long)xo * dy.sx + c);
-        if (kind == 0) {
-          acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
-        } else {
-          const int t = (y - (2 * yo - 1)) * 3 + (x - (2 * xo - 1));
-          const uchar4 am = *reinterpret_cast<const uchar4*>(idx + (((long long)ni * ho + yo) * wo + xo) * (c4 * 4) + c);
-          if (am.x == t) acc.x += g.x;
-          if (am.y == t) acc.y += g.y;
-          if (am.z == t) acc.z += g.z;
-          if (am.w == t) acc.w += g.w;
-        }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int a = k >> 1, b = k & 1;
+      if (kind == 0) {
+        acc.x += g[k].x; acc.y += g[k].y; acc.z += g[k].z; acc.w += g[k].w;
+      } else {
+        const unsigned t = (y - (2 * yo[a] - 1)) * 3 + (x - (2 * xo[b] - 1));
+        if (am[k].x == t) acc.x += g[k].x;
+        if (am[k].y == t) acc.y += g[k].y;
+        if (am[k].z == t) acc.z += g[k].z;
+        if (am[k].w == t) acc.w += g[k].w;
       }
     }
     if (kind == 0) {
       acc.x /= 9.f; acc.y /= 9.f; acc.z /= 9.f; acc.w /= 9.f;
     }
-    if (chan_scale) {
-      const float4 sc = ld4(chan_scale + (long long)ni * (c4 * 4) + c);
-      acc.x *= sc.x; acc.y *= sc.y; acc.z *= sc.z; acc.w *= sc.w;
-    }
-    float* d = dx + (long long)ni * d_sn + (long long)y * d_sy + (long long)x * d_sx + c;
-    if (accumulate) {
-      const float4 o = *reinterpret_cast<const float4*>(d);
-      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-    }
+    acc.x = acc.x * sc.x + old.x; acc.y = acc.y * sc.y + old.y; acc.z = acc.z * sc.z + old.z; acc.w = acc.w * sc.w + old.w;
     *reinterpret_cast<float4*>(d) = acc;
   }
 }
@@ -514,37 +521,69 @@ softmax_nchw_kernel(EpiView lg, int n, int h, int w, int c, float* __restrict__ 
   }
 }
 
+// One thread per pixel: the NCHW reads are coalesced across the warp (consecutive pixels of one channel plane).  The
+// NHWC result of a 256-pixel block is one contiguous run when the destination is dense (d_sx == cpad): it is staged
+// through shared memory and written with fully coalesced stores (a per-thread float4 write at an 80-byte stride ran
+// at 0.7 TB/s).  `dense` = 0 keeps the direct strided write for arbitrary views.
+template <int CMAX>
 __global__ void __launch_bounds__(256)
-softmax_nchw_bwd_kernel(const float* __restrict__ pr, const float* __restrict__ dp, int n, int h, int w, int c, float* dz,
-                        long long d_sn, long long d_sy, long long d_sx, int round_out) {
+softmax_nchw_bwd_kernel(const float* __restrict__ pr, const float* __restrict__ dp, int n, int h, int w, int c, int cpad, float* dz,
+                        long long d_sn, long long d_sy, long long d_sx, int round_out, int dense) {
+  extern __shared__ float s_out[];  // 256 x (cpad | 1)
+  const int pitch = cpad | 1;
   const long long hw = (long long)h * w;
   const long long total = (long long)n * hw;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ni = (int)(i / hw);
-    const long long p = i - (long long)ni * hw;
-    const int y = (int)(p / w), x = (int)(p % w);
-    const float* pp = pr + (long long)ni * c * hw + p;
-    const float* gp = dp + (long long)ni * c * hw + p;
-    float pv[kMaxSoftmaxC], gv[kMaxSoftmaxC];
-    float dot = 0.f;
+  for (long long base = blockIdx.x * 256ll; base < total; base += (long long)gridDim.x * 256ll) {
+    const long long i = base + threadIdx.x;
+    if (i < total) {
+      const int ni = (int)(i / hw);
+      const long long p = i - (long long)ni * hw;
+      const float* pp = pr + (long long)ni * c * hw + p;
+      const float* gp = dp + (long long)ni * c * hw + p;
+      float pv[CMAX], gv[CMAX];
+      float dot = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxSoftmaxC; ++j) {
-      if (j < c) {
-        pv[j] = __ldg(pp + (long long)j * hw);
-        gv[j] = __ldg(gp + (long long)j * hw);
-        dot += pv[j] * gv[j];
+      for (int j = 0; j < CMAX; ++j) {
+        if (j < c) {
+          pv[j] = __ldg(pp + (long long)j * hw);
+          gv[j] = __ldg(gp + (long long)j * hw);
+          dot += pv[j] * gv[j];
+        }
+      }
+      if (dense) {
+#pragma unroll
+        for (int j = 0; j < CMAX; ++j) {
+          if (j < cpad) {
+            float o = j < c ? pv[j] * (gv[j] - dot) : 0.f;
+            if (round_out) o = round_tf32(o);
+            s_out[threadIdx.x * pitch + j] = o;
+          }
+        }
+      } else {
+        const int y = (int)(p / w), x = (int)(p % w);
+        float* d = dz + (long long)ni * d_sn + (long long)y * d_sy + (long long)x * d_sx;
+#pragma unroll
+        for (int j = 0; j < CMAX; j += 4) {
+          if (j < c) {
+            float4 o = make_float4(pv[j] * (gv[j] - dot), j + 1 < c ? pv[j + 1] * (gv[j + 1] - dot) : 0.f,
+                                   j + 2 < c ? pv[j + 2] * (gv[j + 2] - dot) : 0.f,
+                                   j + 3 < c ? pv[j + 3] * (gv[j + 3] - dot) : 0.f);
+            if (round_out) o = rnd4(o);
+            *reinterpret_cast<float4*>(d + j) = o;
+          }
+        }
       }
     }
-    float* d = dz + (long long)ni * d_sn + (long long)y * d_sy + (long long)x * d_sx;
-#pragma unroll
-    for (int j = 0; j < kMaxSoftmaxC; j += 4) {
-      if (j < c) {
-        float4 o = make_float4(pv[j] * (gv[j] - dot), j + 1 < c ? pv[j + 1] * (gv[j + 1] - dot) : 0.f,
-                               j + 2 < c ? pv[j + 2] * (gv[j + 2] - dot) : 0.f,
-                               j + 3 < c ? pv[j + 3] * (gv[j + 3] - dot) : 0.f);
-        if (round_out) o = rnd4(o);
-        *reinterpret_cast<float4*>(d + j) = o;
+    if (dense) {
+      __syncthreads();
+      const long long left = total - base;
+      const int npx = left < 256 ? (int)left : 256;
+      float* d = dz + base * cpad;
+      for (int k = threadIdx.x; k < npx * cpad; k += 256) {
+        const int px = k / cpad, j = k - px * cpad;
+        d[k] = s_out[px * pitch + j];
       }
+      __syncthreads();
     }
   }
 }
@@ -701,6 +740,7 @@ extern "C" int pmfb_pool3s2_bwd(int32_t kind, const pmfb_view* dy, int32_t n, in
   REQ(c % 4 == 0 && h % 2 == 0 && w % 2 == 0 && (kind == 0 || (kind == 1 && idx)), "pool3s2_bwd: bad arguments");
   const long long total = (long long)n * h * w * (c / 4);
   if (total == 0) return PMFB_OK;
+  REQ(total < (1ll << 32), "pool3s2_bwd: tensor too large for 32-bit indexing");
   pool3s2_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(kind, ev(dy), n, h, w, c / 4, chan_scale, dx, d_sn, d_sy,
                                                                              d_sx, idx, accumulate);
   PMFB_LAUNCH_CHECK("pool3s2_bwd_kernel");
@@ -769,8 +809,17 @@ extern "C" int pmfb_softmax_nchw_bwd(const float* p, const float* dp, int32_t n,
   REQ(c > 0 && c <= kMaxSoftmaxC, "softmax_nchw_bwd: c=%d must be in [1,%d]", c, kMaxSoftmaxC);
   const long long total = (long long)n * h * w;
   if (total == 0) return PMFB_OK;
-  softmax_nchw_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(p, dp, n, h, w, c, dz, d_sn, d_sy, d_sx,
-                                                                                  round_out);
+  // dense destination: the row of pixel i starts at i * d_sx for every image/row, and d_sx is the padded channel count
+  const int cpad = (int)d_sx;
+  const int dense = (d_sy == (long long)w * d_sx && d_sn == (long long)h * d_sy && d_sx >= c && d_sx <= kMaxSoftmaxC) ? 1 : 0;
+  const size_t smem = dense ? 256 * (size_t)(cpad | 1) * sizeof(float) : 0;
+  const int grid = grid_for((total + 255) / 256 * 256, 256);
+  if ((dense ? cpad : c) <= 24)  // the 20-class (KITTI) / 17-class (nuScenes) heads: a third of the registers
+    softmax_nchw_bwd_kernel<24><<<grid, 256, smem, (cudaStream_t)stream>>>(p, dp, n, h, w, c, dense ? cpad : c, dz, d_sn, d_sy, d_sx,
+                                                                           round_out, dense);
+  else
+    softmax_nchw_bwd_kernel<kMaxSoftmaxC><<<grid, 256, smem, (cudaStream_t)stream>>>(p, dp, n, h, w, c, dense ? cpad : c, dz, d_sn,
+                                                                                     d_sy, d_sx, round_out, dense);
   PMFB_LAUNCH_CHECK("softmax_nchw_bwd_kernel");
   return PMFB_OK;
 }

@@ -38,6 +38,14 @@ struct WHaloK {
   int tiles_x, tiles_y, n_batch;
   int c_in, c_out, n_tile, n_blocks, c_groups, split;
   int nblk_b;                 // 32-channel dy boxes per stage
+  // Tap packing (c_in <= 32): the four 32-row blocks of the M=128 A operand are up to four TAPS of the same 32-channel
+  // block instead of four channel blocks -- the descriptor's leading byte offset is the (constant) distance between the
+  // taps of a group inside the halo tile -- so a 3x3 layer issues 3 UMMAs per tile row instead of 9.
+  int packed, n_groups;
+  int grp_off[PMFB_MAX_TAPS];      // first tap's window offset inside the halo tile, in pixels (128-byte rows)
+  int grp_lbo[PMFB_MAX_TAPS];      // distance between consecutive taps of the group, in pixels
+  int grp_cnt[PMFB_MAX_TAPS];
+  int grp_tap[PMFB_MAX_TAPS][4];   // weight-gradient slab of each packed tap
   int a_blk_bytes, a_span, b_blk_bytes, stage_bytes, stages, tmem_cols;
   float* dw;
 };
@@ -115,10 +123,11 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_con
         mbar_wait(&ctrl->full[s], (uint32_t)(it / P.stages) & 1u);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(tiles + (size_t)s * P.stage_bytes);
-        const uint32_t a_lo0 = ((a_addr & 0x3FFFFu) >> 4) | lbo_a;
+        const uint32_t a_lo00 = (a_addr & 0x3FFFFu) >> 4;
         const uint32_t b_lo0 = (((a_addr + (uint32_t)P.a_span) & 0x3FFFFu) >> 4) | lbo_b;
-        for (int t = 0; t < P.n_taps; ++t) {
-          const uint32_t a_tap = a_lo0 + (uint32_t)((((P.tap_dh[t] + P.hy) * pitch + P.tap_dw[t] + P.hx) * 128) >> 4);
+        for (int t = 0; t < P.n_groups; ++t) {
+          const uint32_t lbo = P.packed ? ((((uint32_t)P.grp_lbo[t] * 128u) >> 4) & 0x3FFFu) << 16 : lbo_a;
+          const uint32_t a_tap = a_lo00 + lbo + (uint32_t)((P.grp_off[t] * 128) >> 4);
           const uint32_t d_col = tmem_base + (uint32_t)(t * P.n_tile);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {  // one tile row (8 pixels) per K step
@@ -132,12 +141,14 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_con
       umma_commit_warp(&ctrl->tmem_full);
     } else {
       const int q = warp & 3;
-      const int ci = ci0 + q * 32 + lane;
+      const int ci = P.packed ? lane : ci0 + q * 32 + lane;
       const bool valid = ci < P.c_in;
       mbar_wait_sleep(&ctrl->tmem_full, 0);
       tc_fence_after();
-      for (int t = 0; t < P.n_taps; ++t) {
-        float* dst = P.dw + ((long long)t * P.c_in + ci) * P.c_out;
+      for (int t = 0; t < P.n_groups; ++t) {
+        if (P.packed && q >= P.grp_cnt[t]) continue;  // warp-uniform
+        const int tap = P.packed ? P.grp_tap[t][q] : t;
+        float* dst = P.dw + ((long long)tap * P.c_in + ci) * P.c_out;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * P.n_tile);
         for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
           float v[16];
@@ -198,12 +209,65 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
   P.n_batch = d->n_batch;
   P.tiles_x = (d->out_w + 7) / 8;
   P.tiles_y = (d->out_h + 7) / 8;
-  // all taps of one (channel group, output block) live in TMEM: taps * n_tile <= 512 columns
-  int n_tile = (512 / d->n_taps) & ~15;
+  const int pitch = 8 + 2 * P.hx, rows = 8 + 2 * P.hy;
+  // ---- tap groups.  Unpacked: one group per tap.  Packed (c_in <= 32): greedy arithmetic progressions of up to four
+  // window offsets (e.g. the three taps of one 3x3 kernel row: distance = dilation pixels; the 7 vertical taps of the
+  // unrolled stem: distance = one tile row).
+  static int pack_mode = -1;
+  if (pack_mode < 0) {
+    const char* e = getenv("PMFB_WGRAD_PACK");
+    pack_mode = e ? atoi(e) : 1;
+  }
+  P.packed = (pack_mode && d->c_in <= 32 && d->n_taps > 1) ? 1 : 0;
+  P.n_groups = 0;
+  {
+    int off[PMFB_MAX_TAPS], used[PMFB_MAX_TAPS];
+    for (int i = 0; i < d->n_taps; ++i) {
+      off[i] = (d->tap_dh[i] + P.hy) * pitch + d->tap_dw[i] + P.hx;
+      used[i] = 0;
+    }
+    for (;;) {
+      int first = -1;
+      for (int i = 0; i < d->n_taps; ++i)
+        if (!used[i] && (first < 0 || off[i] < off[first])) first = i;
+      if (first < 0) break;
+      const int g = P.n_groups++;
+      used[first] = 1;
+      P.grp_off[g] = off[first];
+      P.grp_cnt[g] = 1;
+      P.grp_lbo[g] = 0;
+      P.grp_tap[g][0] = first;
+      if (!P.packed) continue;
+      int next = -1;
+      for (int i = 0; i < d->n_taps; ++i)
+        if (!used[i] && (next < 0 || off[i] < off[next])) next = i;
+      if (next < 0) continue;
+      const int delta = off[next] - off[first];
+      if (delta <= 0 || delta * 8 > 0x3FFF) continue;
+      int last = off[first];
+      while (P.grp_cnt[g] < 4) {
+        int hit = -1;
+        for (int i = 0; i < d->n_taps; ++i)
+          if (!used[i] && off[i] == last + delta) hit = i;
+        if (hit < 0) break;
+        used[hit] = 1;
+        P.grp_tap[g][P.grp_cnt[g]++] = hit;
+        last += delta;
+      }
+      P.grp_lbo[g] = delta;
+    }
+  }
+  // every group of one (channel group, output block) lives in TMEM: groups * n_tile <= 512 columns
+  int n_tile = (512 / P.n_groups) & ~15;
   if (n_tile > 256) n_tile = 256;
   const int c_out16 = (d->c_out + 15) & ~15;
   if (n_tile > c_out16) n_tile = c_out16;
   if (n_tile < 16) return fail(PMFB_ERR_INVALID, "wgrad halo: too many taps (%d)", d->n_taps);
+  if (!P.packed)  // unpacked order is the tap order (group g == tap g)
+    for (int i = 0; i < d->n_taps; ++i) {
+      P.grp_off[i] = (d->tap_dh[i] + P.hy) * pitch + d->tap_dw[i] + P.hx;
+      P.grp_tap[i][0] = i;
+    }
   {  // balance the output blocks (e.g. 128 -> 3 x 48 rather than 48+48+32)
     const int nbk = (d->c_out + n_tile - 1) / n_tile;
     int bal = (((d->c_out + nbk - 1) / nbk) + 15) & ~15;
@@ -219,7 +283,6 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
   if (split > total_tiles) split = (int)total_tiles;
   P.split = split;
   P.nblk_b = (n_tile + 31) / 32;
-  const int pitch = 8 + 2 * P.hx, rows = 8 + 2 * P.hy;
   P.a_blk_bytes = (rows * pitch * 128 + 1023) & ~1023;
   P.b_blk_bytes = 64 * 128;
   int nblk_a_max = (d->c_in + 31) / 32;
@@ -235,7 +298,7 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
   if (stages < 2) return fail(PMFB_ERR_INVALID, "wgrad halo: stage of %d bytes does not fit twice", P.stage_bytes);
   P.stages = stages;
   int cols = 32;
-  while (cols < d->n_taps * n_tile) cols <<= 1;
+  while (cols < P.n_groups * n_tile) cols <<= 1;
   P.tmem_cols = cols;
   P.dw = d->dw;
 
