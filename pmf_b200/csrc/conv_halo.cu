@@ -25,6 +25,7 @@ constexpr int kHMaxC = 512;       // per-channel epilogue vectors staged in shar
 constexpr int kHCtrlBytes = 1024 + 4 * kHMaxC * 4;
 constexpr int kHMaxB = 8;
 constexpr int kHSmemBudget = 208 * 1024;
+constexpr int kHStageBytes = 4096;  // per epilogue warp: 32 pixels x 32 channels, the source box of one TMA store
 
 struct HCtrl {
   uint64_t full_a[2], empty_a[2];
@@ -39,7 +40,7 @@ struct HaloK {
   int hx, hy, mt;
   int tiles_x, tiles_y, n_batch, n_blocks;
   int out_h, out_w, c_out, n_tile;
-  int nsb, a_bytes, a_box_bytes, nacc, tmem_cols, use_base_off;
+  int nsb, a_bytes, a_box_bytes, nacc, tmem_cols, use_base_off, tma_store;
   float* out;
   long long o_sn, o_sy, o_sx;
   EpiParams epi;
@@ -62,7 +63,7 @@ constexpr int kEpiB1 = 1, kEpiR1 = 2, kEpiRnd = 4, kEpiLeaky = 8;
 template <int EPI>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
-                     const __grid_constant__ HaloK P) {
+                     const __grid_constant__ CUtensorMap tmo, const __grid_constant__ HaloK P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   HCtrl* ctrl = reinterpret_cast<HCtrl*>(smem);
@@ -91,6 +92,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
     fence_proxy_async();
     tma_prefetch_desc(&tmx);
     tma_prefetch_desc(&tmw);
+    if (P.tma_store) tma_prefetch_desc(&tmo);
   }
   if (warp == 1) {
     tmem_alloc(&ctrl->tmem_base, (uint32_t)P.tmem_cols);
@@ -193,6 +195,14 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const float* sv = reinterpret_cast<const float*>(smem + 1024);  // [alpha1 | beta1 | alpha2 | beta2] x kHMaxC
+    // Output path: each warp parks its 32-pixel x 32-channel unit in a private 4 KB staging tile (128B-swizzled rows,
+    // conflict-free 16-byte stores) and one lane issues a bulk tensor store of the (32 ch, 8 x, 4 y) box: full-line
+    // writes, image-edge and channel-tail clipping by the TMA unit.  (Per-thread float4 stores at a 128-byte stride
+    // sustained only ~2 TB/s of stores and doubled the L1->L2 write sectors.)
+    uint8_t* stage = b_buf + (size_t)P.nsb * b_bytes + (size_t)(warp - 2) * kHStageBytes;
+    const uint32_t st_row = smem_u32(stage) + (uint32_t)lane * 128u;
+    const uint32_t st_x = (uint32_t)(lane & 7);
+    const bool tma_store = P.tma_store != 0;
     const bool hA1 = P.epi.alpha1 != nullptr, hB1 = P.epi.beta1 != nullptr, hA2 = P.epi.alpha2 != nullptr,
                hB2 = P.epi.beta2 != nullptr;
     const int chunks = (P.n_tile + 31) >> 5;
@@ -233,6 +243,10 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
             }
           }
           tmem_ld_wait();
+          if (tma_store) {  // the previous unit's store must have finished reading the staging tile
+            if (lane == 0) bulk_wait_group_read0();
+            __syncwarp();
+          }
           if (valid) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -248,8 +262,17 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                   o.z = fmaxf(o.z, 0.01f * o.z); o.w = fmaxf(o.w, 0.01f * o.w);
                 }
                 if constexpr ((EPI & kEpiRnd) != 0) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-                *reinterpret_cast<float4*>(optr + 4 * i) = o;
+                if (tma_store) st_shared_v4(st_row + ((((uint32_t)i) ^ st_x) << 4), o);
+                else *reinterpret_cast<float4*>(optr + 4 * i) = o;
               }
+            }
+          }
+          if (tma_store) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmo, stage, c0, x0, y0 + 16 * j + 4 * q, n_img);
+              bulk_commit_group();
             }
           }
         }
@@ -279,6 +302,10 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
           }
         }
         tmem_ld_wait();
+        if (tma_store) {
+          if (lane == 0) bulk_wait_group_read0();
+          __syncwarp();
+        }
         if (valid) {
           float* optr = P.out + pix_o;
 #pragma unroll
@@ -295,8 +322,17 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
               if (ep.mul) { o.x *= mulv[i].x; o.y *= mulv[i].y; o.z *= mulv[i].z; o.w *= mulv[i].w; }
               if (ep.r2) { o.x += r2v[i].x; o.y += r2v[i].y; o.z += r2v[i].z; o.w += r2v[i].w; }
               if (P.epi.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-              *reinterpret_cast<float4*>(optr + c) = o;
+              if (tma_store) st_shared_v4(st_row + ((((uint32_t)i) ^ st_x) << 4), o);
+              else *reinterpret_cast<float4*>(optr + c) = o;
             }
+          }
+        }
+        if (tma_store) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmo, stage, c0, x0, y0 + 16 * j + 4 * q, n_img);
+            bulk_commit_group();
           }
         }
       }
@@ -304,6 +340,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctrl->tmem_empty[buf]);
     }
+    if (tma_store && lane == 0) bulk_wait_group0();
   }
   tc_fence_before();
   __syncthreads();
@@ -331,25 +368,26 @@ int halo_eligible(const pmfb_conv_desc* d) {
 }
 
 template <int EPI>
-static int launch_halo_t(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& tmx, const CUtensorMap& tmw, const HaloK& P) {
+static int launch_halo_t(int grid, size_t smem, cudaStream_t stream, const CUtensorMap& tmx, const CUtensorMap& tmw,
+                         const CUtensorMap& tmo, const HaloK& P) {
   static bool attr_set = false;
   if (!attr_set) {
     PMFB_CUDA_CHECK(cudaFuncSetAttribute(conv_fwd_halo_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHSmemBudget + 2048));
     attr_set = true;
   }
-  conv_fwd_halo_kernel<EPI><<<grid, kHThreads, smem, stream>>>(tmx, tmw, P);
+  conv_fwd_halo_kernel<EPI><<<grid, kHThreads, smem, stream>>>(tmx, tmw, tmo, P);
   PMFB_LAUNCH_CHECK("conv_fwd_halo_kernel");
   return PMFB_OK;
 }
 
 static int launch_halo_variant(int epi, int grid, size_t smem, cudaStream_t stream, const CUtensorMap& tmx, const CUtensorMap& tmw,
-                               const HaloK& P) {
+                               const CUtensorMap& tmo, const HaloK& P) {
   switch (epi) {
-#define PMFB_HV(e) case e: return launch_halo_t<e>(grid, smem, stream, tmx, tmw, P);
+#define PMFB_HV(e) case e: return launch_halo_t<e>(grid, smem, stream, tmx, tmw, tmo, P);
     PMFB_HV(0) PMFB_HV(1) PMFB_HV(2) PMFB_HV(3) PMFB_HV(4) PMFB_HV(5) PMFB_HV(6) PMFB_HV(7)
     PMFB_HV(8) PMFB_HV(9) PMFB_HV(12) PMFB_HV(13)
 #undef PMFB_HV
-    default: return launch_halo_t<kEpiGeneric>(grid, smem, stream, tmx, tmw, P);
+    default: return launch_halo_t<kEpiGeneric>(grid, smem, stream, tmx, tmw, tmo, P);
   }
 }
 
@@ -389,8 +427,10 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   {
     double best = 1e30;
     const int n_full = n_tile;
-    const int n_cands[3] = {n_full, (n_full % 32 == 0 && n_full >= 128) ? n_full / 2 : 0,
-                            (n_full % 64 == 0 && n_full >= 256) ? n_full / 4 : 0};
+    // split blocks stay multiples of 32 channels: the epilogue's store boxes are 32 channels wide and only the tensor's
+    // own channel count clips them
+    const int n_cands[3] = {n_full, (n_full % 64 == 0 && n_full >= 128) ? n_full / 2 : 0,
+                            (n_full % 128 == 0 && n_full >= 256) ? n_full / 4 : 0};
     const double kdim = 32.0 * P.ks * d->n_taps;
     for (int mi = 2; mi >= 1; --mi)
       for (int ni = 0; ni < 3; ++ni) {
@@ -426,7 +466,16 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   P.a_box_bytes = rows * pitch * 128;
   P.a_bytes = (P.a_box_bytes + 1023) & ~1023;
   const int b_bytes = n_tile * 128;
-  int nsb = (kHSmemBudget - kHCtrlBytes - 2 * P.a_bytes) / b_bytes;
+  static int tma_store_mode = -1;
+  if (tma_store_mode < 0) {
+    const char* e = getenv("PMFB_HALO_TMA_STORE");
+    tma_store_mode = e ? atoi(e) : 1;
+  }
+  // the bulk tensor store needs a 16-byte aligned base and strides; every view the executor builds satisfies this
+  P.tma_store = (tma_store_mode && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && d->o_sx % 4 == 0 && d->o_sy % 4 == 0 &&
+                 d->o_sn % 4 == 0 && (P.n_blocks == 1 || n_tile % 32 == 0)) ? 1 : 0;
+  const int stage_total = P.tma_store ? kHEpiWarps * kHStageBytes : 0;
+  int nsb = (kHSmemBudget - kHCtrlBytes - 2 * P.a_bytes - stage_total) / b_bytes;
   if (nsb > kHMaxB) nsb = kHMaxB;
   if (nsb < 2) return fail(PMFB_ERR_INVALID, "conv halo: shared memory budget exceeded (n_tile=%d)", n_tile);
   if (d->c_out > kHMaxC) return fail(PMFB_ERR_INVALID, "conv halo: c_out=%d > %d", d->c_out, kHMaxC);
@@ -453,7 +502,15 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   rc = make_tmap_f32(&tmw, d->w, 3, wdims, wstr, boxw);
   if (rc) return rc;
 
-  const size_t smem = (size_t)kHCtrlBytes + 2 * (size_t)P.a_bytes + (size_t)nsb * b_bytes + 1024;
+  CUtensorMap tmo = tmw;  // placeholder when the direct-store path is used
+  if (P.tma_store) {
+    uint64_t odims[4] = {(uint64_t)d->c_out, (uint64_t)d->out_w, (uint64_t)d->out_h, (uint64_t)d->n_batch};
+    uint64_t ostr[3] = {(uint64_t)d->o_sx * 4, (uint64_t)d->o_sy * 4, (uint64_t)d->o_sn * 4};
+    uint32_t boxo[4] = {32, 8, 4, 1};
+    rc = make_tmap_f32(&tmo, d->out, 4, odims, ostr, boxo);
+    if (rc) return rc;
+  }
+  const size_t smem = (size_t)kHCtrlBytes + 2 * (size_t)P.a_bytes + (size_t)nsb * b_bytes + stage_total + 1024;
   const long long total = (long long)P.tiles_x * P.tiles_y * P.n_batch * P.n_blocks;
   const int grid = (int)(total < sm_count ? total : sm_count);
   // epilogue variant
@@ -468,7 +525,7 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
       (E.act == PMFB_ACT_NONE || E.act == PMFB_ACT_LEAKY) && !(E.r1.ptr && E.act != PMFB_ACT_NONE)) {
     epi = (E.beta1 ? kEpiB1 : 0) | (E.r1.ptr ? kEpiR1 : 0) | (E.round_out ? kEpiRnd : 0) | (E.act == PMFB_ACT_LEAKY ? kEpiLeaky : 0);
   }
-  return launch_halo_variant(epi, grid, smem, (cudaStream_t)stream, tmx, tmw, P);
+  return launch_halo_variant(epi, grid, smem, (cudaStream_t)stream, tmx, tmw, tmo, P);
 }
 
 }  // namespace pmfb
