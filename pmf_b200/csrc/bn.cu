@@ -7,6 +7,8 @@
 // All reductions share one skeleton: a CTA owns G = min(C/4, 256) float4 channel groups and 256/G pixel lanes,
 // strides over the pixels, keeps fp32 partials that are flushed into fp64 every 64 pixels, reduces the pixel
 // lanes through shared memory and issues one fp64 atomicAdd per channel per CTA.
+#include <stdlib.h>
+
 #include "common.h"
 #include "epilogue.cuh"
 
@@ -338,7 +340,13 @@ static inline RedGrid red_grid(K kernel, long long npix, int c4, int images) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRedThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
   }
   RedGrid r;
-  r.G = c4 < 8 ? c4 : 8;  // <= 32 channels per block: see the block-reduction note in chan_reduce_kernel
+  static int g_cap = 0;
+  if (g_cap == 0) {
+    const char* e = getenv("PMFB_RED_G");
+    g_cap = e ? atoi(e) : 8;
+    if (g_cap < 1 || g_cap > 64 || (g_cap & (g_cap - 1))) g_cap = 8;
+  }
+  r.G = c4 < g_cap ? c4 : g_cap;  // <= 32 channels per block by default: see the block-reduction note in chan_reduce_kernel
   const int L = kRedThreads / r.G;
   const int gy = (c4 + r.G - 1) / r.G;
   long long gx = (npix + (long long)L * 16 - 1) / ((long long)L * 16);  // >= 16 pixels per thread

@@ -417,10 +417,15 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
     }
   }
   P.tiles_x = (d->out_w + 7) / 8;
-  // Tile shape: (MT stacked 128-pixel tiles) x (n_tile output channels) per work item, chosen by a small cost model:
-  //   time ~ waves * max(MMA cycles, L2->SM cycles) with waves = ceil(items / SMs)   (persistent CTAs: the last wave's
-  //   fill matters on the low-resolution layers, the weight re-fetch per item on the wide ones).
-  // Per-SM rates: ~3900 tf32 FLOP/cycle (1.1 PFLOP/s / 148 SMs / 1.9 GHz), ~43 B/cycle of TMA fill (B300 guide).
+  // Tile shape: (MT stacked 128-pixel tiles) x (n_tile output channels) per work item, chosen by a cost model fitted
+  // to measurements on B200 (profiles/r1_halo_model.md):
+  //   * one kind::tf32 UMMA (M=128, N=n, K=8, both operands in shared memory) occupies the tensor pipe for
+  //     (128 + n) / 2 cycles: the operand fetch (128 + n rows x 32 B at 64 B/clk), not the math (n / 2), is the limiter,
+  //     so the widest n_tile always wins on MMA time and stacking tiles (MT) only amortises the weight fetch;
+  //   * an item also needs its L2->SM fill (~43 B/clk) and its epilogue (TMEM -> staging -> bulk store); with two
+  //     TMEM accumulator sets (2*MT*n_tile <= 512 columns) these overlap the next item's MMAs, otherwise the
+  //     epilogue is serialised behind them;
+  //   * persistent CTAs walk the item list round-robin: time = ceil(items / SMs) * item time.
   const int c_out16 = ((d->c_out + 15) / 16) * 16;
   int n_tile = c_out16 < 256 ? c_out16 : 256;
   int mt = 2;
@@ -431,19 +436,21 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
     // own channel count clips them
     const int n_cands[3] = {n_full, (n_full % 64 == 0 && n_full >= 128) ? n_full / 2 : 0,
                             (n_full % 128 == 0 && n_full >= 256) ? n_full / 4 : 0};
-    const double kdim = 32.0 * P.ks * d->n_taps;
+    const double ksteps = 4.0 * P.ks * d->n_taps;
     for (int mi = 2; mi >= 1; --mi)
       for (int ni = 0; ni < 3; ++ni) {
         const int nt = n_cands[ni];
         if (nt == 0 || mi * nt > 512) continue;
         const long long items = (long long)P.tiles_x * ((d->out_h + 16 * mi - 1) / (16 * mi)) * d->n_batch * ((d->c_out + nt - 1) / nt);
         const long long waves = (items + sm_count - 1) / sm_count;
-        // measured tensor-pipe efficiency of this kernel by MMA width (conv_launches_r1h): N<=32 0.17, 64 0.33, >=128 0.52
-        const double eff_n = nt <= 32 ? 0.17 : (nt <= 64 ? 0.33 : (nt < 128 ? 0.42 : 0.52));
-        const double mma = 2.0 * 128.0 * mi * nt * kdim / 3900.0 / (eff_n * (mi == 2 ? 1.0 : 0.85));
-        const double bytes = kdim * 4.0 * nt + (double)P.ks * (16 * mi + 2 * P.hy) * (8 + 2 * P.hx) * 128.0;
-        const double mem = bytes / 43.0;
-        const double item = (mma > mem ? mma : mem) + 1500.0 + 6.0 * mi * nt;  // + fixed latency and epilogue
+        // + ~200 cycles per (slab, tap): barrier round trip and descriptor arithmetic of the issuing warp that the
+        // tensor pipe does not hide (fitted: 64-channel layers lose 30 % with MT=1, 256-channel ones gain 25 %)
+        const double mma = ksteps * mi * (128.0 + nt) * 0.5 + 200.0 * P.ks * d->n_taps;
+        const double bytes = ksteps * 8.0 * 4.0 * nt + (double)P.ks * (16 * mi + 2 * P.hy) * (8 + 2 * P.hx) * 128.0;
+        const double fill = bytes / 43.0;
+        const double epi = 400.0 + mi * 128.0 * nt * 4.0 / 24.0;
+        const double body = mma > fill ? mma : fill;
+        const double item = (2 * mi * nt <= 512 ? (body > epi ? body : epi) : body + epi) + 600.0;
         const double cost = (double)waves * item;
         if (cost < best) {
           best = cost;
