@@ -127,7 +127,7 @@ chan_reduce_kernel(F f, unsigned npix, unsigned hw, unsigned w, int c4, int G, i
 }
 
 struct StatsF {
-  static constexpr int kUnroll = 4;
+  static constexpr int kUnroll = 8;
   PV x;
   struct Loaded { float4 v; };
   struct Consts {};
@@ -142,7 +142,7 @@ struct StatsF {
 };
 
 struct ColsumF {
-  static constexpr int kUnroll = 4;
+  static constexpr int kUnroll = 8;
   PV x;
   struct Loaded { float4 v; };
   struct Consts {};
@@ -165,6 +165,9 @@ __device__ __forceinline__ float act_grad(int act, float z) {
 }
 
 // g = dy * mul * act'(z); z is either stored (zv) or recomputed as act(alpha*x + beta) (sigmoid gate).
+// MUL / ZST (stored z) are compile-time: a launch without them (the plain conv -> LeakyReLU -> BN backward, most of the
+// bytes) carries two operand streams, keeps four pixels of loads in flight per thread and has no dead registers.
+template <bool MUL, bool ZST>
 struct GradIn {
   PV dy, mul, z, x;
   const float* mean;
@@ -172,27 +175,27 @@ struct GradIn {
   const float* alpha;
   const float* beta;
   int act_z;
-  struct Loaded { float4 g, m, zz, xv; };
+  struct Loaded { float4 g, xv, m[MUL ? 1 : 0], zz[ZST ? 1 : 0]; };
   struct Consts { float4 mu, is, a, b; };
   __device__ __forceinline__ void prep(int c, Consts& k) const {
     k.mu = k.is = k.a = k.b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (mean) { k.mu = ld4(mean + c); k.is = ld4(invstd + c); }
-    if (act_z && !z.p) { k.a = ld4(alpha + c); k.b = ld4(beta + c); }
+    if (!ZST && act_z) { k.a = ld4(alpha + c); k.b = ld4(beta + c); }
   }
   __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const {
     l.g = ld4(pv_at(dy, pix, hw, w, c));
-    if (mul.p) l.m = ld4(pv_at(mul, pix, hw, w, c));
+    if constexpr (MUL) l.m[0] = ld4(pv_at(mul, pix, hw, w, c));
     if (x.p) l.xv = ld4(pv_at(x, pix, hw, w, c));
-    if (act_z && z.p) l.zz = ld4(pv_at(z, pix, hw, w, c));
+    if constexpr (ZST) l.zz[0] = ld4(pv_at(z, pix, hw, w, c));
   }
   __device__ __forceinline__ void finish(const Consts& k, const Loaded& l, float4& g, float4& xhat, float4& xv) const {
     g = l.g;
-    if (mul.p) { g.x *= l.m.x; g.y *= l.m.y; g.z *= l.m.z; g.w *= l.m.w; }
+    if constexpr (MUL) { g.x *= l.m[0].x; g.y *= l.m[0].y; g.z *= l.m[0].z; g.w *= l.m[0].w; }
     xv = x.p ? l.xv : make_float4(0.f, 0.f, 0.f, 0.f);
     if (act_z) {
       float4 zz;
-      if (z.p) {
-        zz = l.zz;
+      if constexpr (ZST) {
+        zz = l.zz[0];
       } else {
         const float4 a = k.a, b = k.b;
         zz = make_float4(epi_act(act_z, a.x * xv.x + b.x), epi_act(act_z, a.y * xv.y + b.y),
@@ -210,11 +213,12 @@ struct GradIn {
   }
 };
 
+template <bool MUL, bool ZST>
 struct BnBwdReduceF {
-  static constexpr int kUnroll = 2;
-  GradIn in;
-  typedef GradIn::Loaded Loaded;
-  typedef GradIn::Consts Consts;
+  static constexpr int kUnroll = (MUL || ZST) ? 2 : 4;
+  GradIn<MUL, ZST> in;
+  typedef typename GradIn<MUL, ZST>::Loaded Loaded;
+  typedef typename GradIn<MUL, ZST>::Consts Consts;
   __device__ __forceinline__ void prep(int c, Consts& k) const { in.prep(c, k); }
   __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const { in.load(pix, hw, w, c, l); }
   __device__ __forceinline__ void consume(unsigned, unsigned, unsigned, int, const Consts& k, const Loaded& l, RedAcc<2>& a) const {
@@ -227,18 +231,19 @@ struct BnBwdReduceF {
 
 // With BN (in.mean != NULL): dx = gamma*invstd*(g - S1/M - xhat*S2/M) [* leaky'(x)].
 // Without BN: dx = g [* leaky'(x)]   (plain activation backward, e.g. the conv->LeakyReLU shortcuts).
+// GACC: g_out is accumulated into (its old value is one more operand stream).
+template <bool MUL, bool ZST, bool GACC>
 struct BnBwdApplyF {
-  static constexpr int kUnroll = 2;
-  GradIn in;
+  static constexpr int kUnroll = (MUL || ZST || GACC) ? 2 : 4;
+  GradIn<MUL, ZST> in;
   const float* gamma;
   const double* red;
   double inv_count;
   int C, leaky_x, round_out;
   PV dx;
   PV g_out;
-  int g_accumulate;
-  struct Loaded { GradIn::Loaded i; float4 e; };
-  struct Consts { GradIn::Consts i; float4 gi, m1, m2; };
+  struct Loaded { typename GradIn<MUL, ZST>::Loaded i; float4 e[GACC ? 1 : 0]; };
+  struct Consts { typename GradIn<MUL, ZST>::Consts i; float4 gi, m1, m2; };
   __device__ __forceinline__ void prep(int c, Consts& k) const {
     in.prep(c, k.i);
     k.gi = k.m1 = k.m2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -253,7 +258,7 @@ struct BnBwdApplyF {
   }
   __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const {
     in.load(pix, hw, w, c, l.i);
-    if (g_out.p && g_accumulate) l.e = ld4(pv_at(g_out, pix, hw, w, c));
+    if constexpr (GACC) l.e[0] = ld4(pv_at(g_out, pix, hw, w, c));
   }
   __device__ __forceinline__ void consume(unsigned pix, unsigned hw, unsigned w, int c, const Consts& k, const Loaded& l,
                                           RedAcc<1>& a) const {
@@ -261,7 +266,7 @@ struct BnBwdApplyF {
     in.finish(k.i, l.i, g, xh, xv);
     if (g_out.p) {
       float4 o = g;
-      if (g_accumulate) { o.x += l.e.x; o.y += l.e.y; o.z += l.e.z; o.w += l.e.w; }
+      if constexpr (GACC) { o.x += l.e[0].x; o.y += l.e[0].y; o.z += l.e[0].z; o.w += l.e[0].w; }
       *reinterpret_cast<float4*>(const_cast<float*>(pv_at(g_out, pix, hw, w, c))) = o;
     }
     float4 d = g;
@@ -404,7 +409,8 @@ extern "C" int pmfb_bn_finalize(const double* sums, int64_t count, int32_t c, co
   return PMFB_OK;
 }
 
-static int fill_grad_in(GradIn* gi, const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int act_z,
+template <class GI>
+static int fill_grad_in(GI* gi, const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int act_z,
                         const pmfb_view* x, const float* mean, const float* invstd, const float* alpha, const float* beta,
                         int h, int w) {
   if (!dy || !dy->ptr || !vok(dy) || !vok(mul) || !vok(z) || !vok(x)) return fail(PMFB_ERR_INVALID, "bn_bwd: bad views");
@@ -425,21 +431,76 @@ static int fill_grad_in(GradIn* gi, const pmfb_view* dy, const pmfb_view* mul, c
   return PMFB_OK;
 }
 
+template <bool MUL, bool ZST>
+static int bn_bwd_reduce_t(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z, const pmfb_view* x,
+                           const float* mean, const float* invstd, const float* alpha, const float* beta, int32_t n, int32_t h,
+                           int32_t w, int32_t c, double* red, void* stream) {
+  typedef BnBwdReduceF<MUL, ZST> F;
+  F f;
+  int rc = fill_grad_in(&f.in, dy, mul, z, act_z, x, mean, invstd, alpha, beta, h, w);
+  if (rc) return rc;
+  const long long npix = (long long)n * h * w;
+  if (npix == 0) return PMFB_OK;
+  RedGrid g = red_grid(chan_reduce_kernel<2, F>, npix, c / 4, 1);
+  chan_reduce_kernel<2, F><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, (unsigned)npix, (unsigned)(h * w), (unsigned)w, c / 4,
+                                                                             g.G, 0, red);
+  PMFB_LAUNCH_CHECK("bn_bwd_reduce");
+  return PMFB_OK;
+}
+
+struct ApplyArgs {
+  const pmfb_view *dy, *mul, *z, *x;
+  int act_z;
+  const float *mean, *invstd, *alpha, *beta, *gamma;
+  const double* red;
+  int leaky_x, n, h, w, c;
+  float* dx;
+  long long d_sn, d_sy, d_sx;
+  int round_out;
+  float *dgamma, *dbeta;
+  double* colsum;
+  float* g_out;
+  long long g_sn, g_sy, g_sx;
+  void* stream;
+};
+
+template <bool MUL, bool ZST, bool GACC>
+static int bn_bwd_apply_t(const ApplyArgs& A) {
+  typedef BnBwdApplyF<MUL, ZST, GACC> F;
+  F f;
+  int rc = fill_grad_in(&f.in, A.dy, A.mul, A.z, A.act_z, A.x, A.mean, A.invstd, A.alpha, A.beta, A.h, A.w);
+  if (rc) return rc;
+  const long long npix = (long long)A.n * A.h * A.w;
+  if (npix == 0) return PMFB_OK;
+  f.gamma = A.gamma;
+  f.red = A.red;
+  f.inv_count = 1.0 / (double)npix;
+  f.C = A.c;
+  f.leaky_x = A.leaky_x;
+  f.round_out = A.round_out;
+  f.dx = pv_out(A.dx, A.d_sn, A.d_sy, A.d_sx, A.h, A.w);
+  f.g_out = pv_out(A.g_out, A.g_sn, A.g_sy, A.g_sx, A.h, A.w);
+  RedGrid g = red_grid(chan_reduce_kernel<1, F>, npix, A.c / 4, 1);
+  chan_reduce_kernel<1, F><<<g.grid, kRedThreads, 0, (cudaStream_t)A.stream>>>(f, (unsigned)npix, (unsigned)(A.h * A.w), (unsigned)A.w,
+                                                                               A.c / 4, g.G, 0, A.colsum);
+  PMFB_LAUNCH_CHECK("bn_bwd_apply");
+  if (A.mean && (A.dgamma || A.dbeta)) {
+    red_to_params_kernel<<<(A.c + 127) / 128, 128, 0, (cudaStream_t)A.stream>>>(A.red, A.c, A.dgamma, A.dbeta);
+    PMFB_LAUNCH_CHECK("red_to_params");
+  }
+  return PMFB_OK;
+}
+
 extern "C" int pmfb_bn_bwd_reduce(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z,
                                   const pmfb_view* x, const float* mean, const float* invstd, const float* alpha,
                                   const float* beta, int32_t n, int32_t h, int32_t w, int32_t c, double* red,
                                   void* stream) {
   REQ(red && mean && c > 0 && c % 4 == 0, "bn_bwd_reduce: bad arguments");
-  BnBwdReduceF f;
-  int rc = fill_grad_in(&f.in, dy, mul, z, act_z, x, mean, invstd, alpha, beta, h, w);
-  if (rc) return rc;
-  const long long npix = (long long)n * h * w;
-  if (npix == 0) return PMFB_OK;
-  RedGrid g = red_grid(chan_reduce_kernel<2, BnBwdReduceF>, npix, c / 4, 1);
-  chan_reduce_kernel<2, BnBwdReduceF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, (unsigned)npix, (unsigned)(h * w),
-                                                                                        (unsigned)w, c / 4, g.G, 0, red);
-  PMFB_LAUNCH_CHECK("bn_bwd_reduce");
-  return PMFB_OK;
+  const bool has_mul = mul && mul->ptr, has_z = act_z && z && z->ptr;
+  if (has_mul) return has_z ? bn_bwd_reduce_t<true, true>(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c, red, stream)
+                            : bn_bwd_reduce_t<true, false>(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c, red, stream);
+  return has_z ? bn_bwd_reduce_t<false, true>(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c, red, stream)
+               : bn_bwd_reduce_t<false, false>(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c, red, stream);
 }
 
 extern "C" int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z,
@@ -454,27 +515,17 @@ extern "C" int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, cons
   REQ(!dx || ((((d_sn | d_sy | d_sx) % 4) == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0)), "bn_bwd_apply: bad dx view");
   REQ(!g_out || ((((g_sn | g_sy | g_sx) % 4) == 0) && ((reinterpret_cast<uintptr_t>(g_out) & 15) == 0)),
       "bn_bwd_apply: bad g_out view");
-  BnBwdApplyF f;
-  int rc = fill_grad_in(&f.in, dy, mul, z, act_z, x, mean, invstd, alpha, beta, h, w);
-  if (rc) return rc;
-  const long long npix = (long long)n * h * w;
-  if (npix == 0) return PMFB_OK;
-  f.gamma = gamma;
-  f.red = red;
-  f.inv_count = 1.0 / (double)npix;
-  f.C = c;
-  f.leaky_x = leaky_x;
-  f.round_out = round_out;
-  f.dx = pv_out(dx, d_sn, d_sy, d_sx, h, w);
-  f.g_out = pv_out(g_out, g_sn, g_sy, g_sx, h, w);
-  f.g_accumulate = g_accumulate;
-  RedGrid g = red_grid(chan_reduce_kernel<1, BnBwdApplyF>, npix, c / 4, 1);
-  chan_reduce_kernel<1, BnBwdApplyF><<<g.grid, kRedThreads, 0, (cudaStream_t)stream>>>(f, (unsigned)npix, (unsigned)(h * w),
-                                                                                       (unsigned)w, c / 4, g.G, 0, colsum);
-  PMFB_LAUNCH_CHECK("bn_bwd_apply");
-  if (mean && (dgamma || dbeta)) {
-    red_to_params_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(red, c, dgamma, dbeta);
-    PMFB_LAUNCH_CHECK("red_to_params");
+  ApplyArgs A{dy, mul, z, x, act_z, mean, invstd, alpha, beta, gamma, red, leaky_x, n, h, w, c, dx, d_sn, d_sy, d_sx, round_out,
+              dgamma, dbeta, colsum, g_out, g_sn, g_sy, g_sx, stream};
+  const int key = ((mul && mul->ptr) ? 4 : 0) | ((act_z && z && z->ptr) ? 2 : 0) | ((g_out && g_accumulate) ? 1 : 0);
+  switch (key) {
+    case 0: return bn_bwd_apply_t<false, false, false>(A);
+    case 1: return bn_bwd_apply_t<false, false, true>(A);
+    case 2: return bn_bwd_apply_t<false, true, false>(A);
+    case 3: return bn_bwd_apply_t<false, true, true>(A);
+    case 4: return bn_bwd_apply_t<true, false, false>(A);
+    case 5: return bn_bwd_apply_t<true, false, true>(A);
+    case 6: return bn_bwd_apply_t<true, true, false>(A);
+    default: return bn_bwd_apply_t<true, true, true>(A);
   }
-  return PMFB_OK;
 }

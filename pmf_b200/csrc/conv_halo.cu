@@ -441,6 +441,10 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
       for (int ni = 0; ni < 3; ++ni) {
         const int nt = n_cands[ni];
         if (nt == 0 || mi * nt > 512) continue;
+        // shared memory: two halo tiles + >= 2 weight stages + the epilogue staging tiles must fit
+        const int a_b = ((16 * mi + 2 * P.hy) * (8 + 2 * P.hx) * 128 + 1023) & ~1023;
+        const int nb_fit = (kHSmemBudget - kHCtrlBytes - 2 * a_b - kHEpiWarps * kHStageBytes) / (nt * 128);
+        if (nb_fit < 2) continue;
         const long long items = (long long)P.tiles_x * ((d->out_h + 16 * mi - 1) / (16 * mi)) * d->n_batch * ((d->c_out + nt - 1) / nt);
         const long long waves = (items + sm_count - 1) / sm_count;
         // + ~200 cycles per (slab, tap): barrier round trip and descriptor arithmetic of the issuing warp that the
@@ -451,7 +455,7 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
         const double epi = 400.0 + mi * 128.0 * nt * 4.0 / 24.0;
         const double body = mma > fill ? mma : fill;
         const double item = (2 * mi * nt <= 512 ? (body > epi ? body : epi) : body + epi) + 600.0;
-        const double cost = (double)waves * item;
+        const double cost = (double)waves * item * (nb_fit < 4 ? 1.1 : 1.0);  // a 2-3 deep weight ring exposes L2 latency
         if (cost < best) {
           best = cost;
           mt = mi;

@@ -42,6 +42,7 @@ struct WHaloK {
   // block instead of four channel blocks -- the descriptor's leading byte offset is the (constant) distance between the
   // taps of a group inside the halo tile -- so a 3x3 layer issues 3 UMMAs per tile row instead of 9.
   int packed, n_groups;
+  int gps, tsplits;                // tap groups per CTA and the number of such tap ranges (TMEM holds gps * n_tile columns)
   int grp_off[PMFB_MAX_TAPS];      // first tap's window offset inside the halo tile, in pixels (128-byte rows)
   int grp_lbo[PMFB_MAX_TAPS];      // distance between consecutive taps of the group, in pixels
   int grp_cnt[PMFB_MAX_TAPS];
@@ -63,8 +64,10 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_con
   const int pitch = 8 + 2 * P.hx;
 
   // CTA -> (group, split index); group -> (channel group, output block)
-  const int grp = blockIdx.x / P.split, sidx = blockIdx.x - grp * P.split;
+  const int grp0 = blockIdx.x / P.split, sidx = blockIdx.x - grp0 * P.split;
+  const int grp = grp0 / P.tsplits, ts = grp0 - grp * P.tsplits;
   const int cg = grp / P.n_blocks, nb = grp - cg * P.n_blocks;
+  const int g_begin = ts * P.gps, g_end = min(g_begin + P.gps, P.n_groups);
   const int ci0 = cg * 128, n0 = nb * P.n_tile;
   int nblk_a = (P.c_in - ci0 + 31) / 32;
   if (nblk_a > 4) nblk_a = 4;
@@ -125,10 +128,10 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_con
         const uint32_t a_addr = smem_u32(tiles + (size_t)s * P.stage_bytes);
         const uint32_t a_lo00 = (a_addr & 0x3FFFFu) >> 4;
         const uint32_t b_lo0 = (((a_addr + (uint32_t)P.a_span) & 0x3FFFFu) >> 4) | lbo_b;
-        for (int t = 0; t < P.n_groups; ++t) {
+        for (int t = g_begin; t < g_end; ++t) {
           const uint32_t lbo = P.packed ? ((((uint32_t)P.grp_lbo[t] * 128u) >> 4) & 0x3FFFu) << 16 : lbo_a;
           const uint32_t a_tap = a_lo00 + lbo + (uint32_t)((P.grp_off[t] * 128) >> 4);
-          const uint32_t d_col = tmem_base + (uint32_t)(t * P.n_tile);
+          const uint32_t d_col = tmem_base + (uint32_t)((t - g_begin) * P.n_tile);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {  // one tile row (8 pixels) per K step
             const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_tap + (uint32_t)(ks * pitch * 8));
@@ -145,11 +148,11 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_con
       const bool valid = ci < P.c_in;
       mbar_wait_sleep(&ctrl->tmem_full, 0);
       tc_fence_after();
-      for (int t = 0; t < P.n_groups; ++t) {
+      for (int t = g_begin; t < g_end; ++t) {
         if (P.packed && q >= P.grp_cnt[t]) continue;  // warp-uniform
         const int tap = P.packed ? P.grp_tap[t][q] : t;
         float* dst = P.dw + ((long long)tap * P.c_in + ci) * P.c_out;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * P.n_tile);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((t - g_begin) * P.n_tile);
         for (int c0 = 0; c0 < P.n_tile; c0 += 16) {
           float v[16];
           tmem_ld16(taddr + (uint32_t)c0, v);
@@ -257,26 +260,66 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
       P.grp_lbo[g] = delta;
     }
   }
-  // every group of one (channel group, output block) lives in TMEM: groups * n_tile <= 512 columns
-  int n_tile = (512 / P.n_groups) & ~15;
-  if (n_tile > 256) n_tile = 256;
+  // Every tap group a CTA owns lives in TMEM: gps * n_tile <= 512 columns.  One UMMA (M=128, N=n, K=8) costs about
+  // (128 + n) / 2 cycles of operand fetch, i.e. (128 + n) / (2 n) cycles per accumulator column: with all nine taps of a
+  // 3x3 kernel in one CTA n_tile is 48 (1.8 cycles/column); giving a CTA one kernel row (gps = 3) allows n_tile = 128-160
+  // (1.0) at the price of fetching the x / dy tiles once per tap range.  Pick the split with the smallest
+  // max(MMA, L2->SM fill) time.
   const int c_out16 = (d->c_out + 15) & ~15;
-  if (n_tile > c_out16) n_tile = c_out16;
-  if (n_tile < 16) return fail(PMFB_ERR_INVALID, "wgrad halo: too many taps (%d)", d->n_taps);
-  if (!P.packed)  // unpacked order is the tap order (group g == tap g)
-    for (int i = 0; i < d->n_taps; ++i) {
-      P.grp_off[i] = (d->tap_dh[i] + P.hy) * pitch + d->tap_dw[i] + P.hx;
-      P.grp_tap[i][0] = i;
+  const int c_groups = (d->c_in + 127) / 128;
+  int nblk_a_max = (d->c_in + 31) / 32;
+  if (nblk_a_max > 4) nblk_a_max = 4;
+  const int a_blk = (rows * pitch * 128 + 1023) & ~1023;
+  int n_tile = 0, gps = P.n_groups;
+  {
+    double best = 1e30;
+    const int cands[4] = {P.n_groups, 3, 2, 1};
+    for (int ci = 0; ci < 4; ++ci) {
+      const int g = cands[ci];
+      if (g > P.n_groups || (ci > 0 && g == P.n_groups)) continue;
+      int nt = (512 / g) & ~15;
+      if (nt > 256) nt = 256;
+      if (nt > c_out16) nt = c_out16;
+      if (nt < 16) continue;
+      const int nbk = (d->c_out + nt - 1) / nt;
+      const int bal = (((d->c_out + nbk - 1) / nbk) + 15) & ~15;  // balance the output blocks (128 -> 3 x 48, not 48+48+32)
+      if (bal < nt) nt = bal;
+      const int tsp = (P.n_groups + g - 1) / g;
+      // shared memory: at least two (x halo blocks + dy blocks) stages, three preferred
+      const int stage_b = nblk_a_max * a_blk + ((nt + 31) / 32) * 8192;
+      const int st_fit = (kWSmemBudget - kWCtrlBytes - (4 - nblk_a_max) * a_blk) / stage_b;
+      if (st_fit < 2) continue;
+      const double mma = (double)c_groups * nbk * P.n_groups * 8.0 * (128.0 + nt) * 0.5;
+      const double fill = (double)c_groups * nbk * tsp * (nblk_a_max * (double)a_blk + ((nt + 31) / 32) * 8192.0) / 43.0;
+      const double cost = ((mma > fill ? mma : fill) + 0.25 * (mma > fill ? fill : mma)) * (st_fit < 3 ? 1.15 : 1.0);
+      if (cost < best) {
+        best = cost;
+        n_tile = nt;
+        gps = g;
+      }
     }
-  {  // balance the output blocks (e.g. 128 -> 3 x 48 rather than 48+48+32)
+  }
+  if (n_tile < 16) return fail(PMFB_ERR_INVALID, "wgrad halo: too many taps (%d)", d->n_taps);
+  static int gps_override = -1;
+  if (gps_override < 0) {
+    const char* e = getenv("PMFB_WGRAD_GPS");
+    gps_override = e ? atoi(e) : 0;
+  }
+  if (gps_override == 99) {  // the previous behaviour: every tap group in one CTA
+    gps = P.n_groups;
+    n_tile = (512 / P.n_groups) & ~15;
+    if (n_tile > 256) n_tile = 256;
+    if (n_tile > c_out16) n_tile = c_out16;
     const int nbk = (d->c_out + n_tile - 1) / n_tile;
-    int bal = (((d->c_out + nbk - 1) / nbk) + 15) & ~15;
+    const int bal = (((d->c_out + nbk - 1) / nbk) + 15) & ~15;
     if (bal < n_tile) n_tile = bal;
   }
+  P.gps = gps;
+  P.tsplits = (P.n_groups + gps - 1) / gps;
   P.n_tile = n_tile;
   P.n_blocks = (d->c_out + n_tile - 1) / n_tile;
   P.c_groups = (d->c_in + 127) / 128;
-  const int groups = P.n_blocks * P.c_groups;
+  const int groups = P.n_blocks * P.c_groups * P.tsplits;
   const long long total_tiles = (long long)P.tiles_x * P.tiles_y * P.n_batch;
   int split = sm_count / groups;
   if (split < 1) split = 1;
@@ -285,8 +328,6 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
   P.nblk_b = (n_tile + 31) / 32;
   P.a_blk_bytes = (rows * pitch * 128 + 1023) & ~1023;
   P.b_blk_bytes = 64 * 128;
-  int nblk_a_max = (d->c_in + 31) / 32;
-  if (nblk_a_max > 4) nblk_a_max = 4;
   // Only the channel blocks that exist are loaded and given shared memory; the A descriptor still spans four blocks
   // (LBO = a_blk_bytes), so for c_in < 128 its upper rows read whatever follows (dy tile / next stage / tail pad):
   // those accumulator rows are never flushed, and every D row depends on its own A row only.
@@ -298,7 +339,7 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
   if (stages < 2) return fail(PMFB_ERR_INVALID, "wgrad halo: stage of %d bytes does not fit twice", P.stage_bytes);
   P.stages = stages;
   int cols = 32;
-  while (cols < P.n_groups * n_tile) cols <<= 1;
+  while (cols < P.gps * n_tile) cols <<= 1;
   P.tmem_cols = cols;
   P.dw = d->dw;
 
