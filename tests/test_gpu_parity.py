@@ -361,6 +361,80 @@ def test_pmf_frame_parallel_and_full_size(dev):
     assert torch.equal(lid[1:2], lid1) and torch.equal(cam[1:2], cam1)  # bit-identical: no cross-frame arithmetic
 
 
+def _miou(pred, label, nclasses, ignore=(0,)):
+    """mean IoU as pc_processor/metrics/iou_eval.py:31-82 computes it (confusion matrix rows = prediction, columns =
+    ground truth, ignored classes' rows and columns zeroed, mean over the included classes, union + 1e-15)."""
+    conf = np.zeros((nclasses, nclasses), dtype=np.float64)
+    np.add.at(conf, (pred.reshape(-1), label.reshape(-1)), 1.0)
+    for c in ignore:
+        conf[c, :] = 0
+        conf[:, c] = 0
+    tp = np.diag(conf)
+    fp, fn = conf.sum(1) - tp, conf.sum(0) - tp
+    inc = [c for c in range(nclasses) if c not in ignore]
+    return float((tp[inc] / (tp[inc] + fp[inc] + fn[inc] + 1e-15)).mean())
+
+
+def test_pmf_miou_on_synthetic_labels_within_0p1pt(dev):
+    """with identical weights the mIoU of our argmax predictions on the synthetic labels is within 0.1 pt
+    (0.001) of the reference arithmetic's, for both heads; the argmax flip rate is reported.  A few training steps first
+    so that the predictions are not uniform noise."""
+    m, _ = _model(dev)
+    feat, mask, _ = synth.frame_tensor(2, 96, 160, seed=91, density=0.5)
+    # learnable synthetic labels: 19 depth bins on the occupied pixels, 0 (ignored) on the empty ones
+    label = ((1 + torch.clamp(((feat[:, 0] + 0.82) / 4.72 * 19).floor(), 0, 18)) * mask).long()
+    x, y = feat.to(dev), label.to(dev)
+    opt = torch.optim.Adam(m.parameters(), lr=2e-3)
+    m.train()
+    for mod in m.modules():  # let the running statistics follow the short fit, and keep it deterministic
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.momentum = 0.5
+        if isinstance(mod, torch.nn.Dropout2d):
+            mod.eval()
+    for _ in range(40):
+        lid, cam = m(x[:, 0:5], x[:, 5:8])
+        t = y.unsqueeze(1)
+        loss = -(torch.log(lid.gather(1, t).clamp_min(1e-8)).mean() + torch.log(cam.gather(1, t).clamp_min(1e-8)).mean())
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    m.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        lid, cam = m(x[:, 0:5], x[:, 5:8])
+        rl, rc = po.pmf_forward(sd, feat[:, 0:5], feat[:, 5:8], "resnet34")
+    rep = {}
+    lab = label.numpy()
+    for name, ours, ref in (("lidar", lid, rl), ("camera", cam, rc)):
+        a, b = ours.cpu().argmax(1).numpy(), ref.argmax(1).numpy()
+        mi_a, mi_b = _miou(a, lab, 20), _miou(b, lab, 20)
+        rep[name] = dict(miou_ours=mi_a, miou_reference=mi_b, flip_rate=float((a != b).mean()), maxrel=_maxrel(ours.cpu(), ref))
+        assert abs(mi_a - mi_b) < 1e-3, rep
+    _report("pmf/miou_synthetic_labels", rep)
+
+
+def test_pmf_resnet50_nuscenes_shaped(dev):
+    """BASELINE config 4 (PMF-ResNet50, 17 classes): eval forward within 1e-3 of the fp32 reference arithmetic and one
+    train step with finite gradients for every one of the Bottleneck-encoder parameters."""
+    m, sd = _model(dev, "resnet50", 17)
+    feat, _, label = synth.frame_tensor(1, 64, 96, seed=17)
+    x = feat.to(dev)
+    m.eval()
+    with torch.no_grad():
+        lid, cam = m(x[:, 0:5], x[:, 5:8])
+        rl, rc = po.pmf_forward(sd, feat[:, 0:5], feat[:, 5:8], "resnet50")
+    assert lid.shape == (1, 17, 64, 96)
+    e = (_maxrel(lid.cpu(), rl), _maxrel(cam.cpu(), rc))
+    _report("pmf/resnet50_eval", dict(lidar=e[0], camera=e[1]))
+    assert e[0] < 1e-3 and e[1] < 1e-3, e
+    m.train()
+    lid, cam = m(x[:, 0:5], x[:, 5:8])
+    t = (label.to(dev) % 17).unsqueeze(1)
+    loss = -(torch.log(lid.gather(1, t).clamp_min(1e-8)).mean() + torch.log(cam.gather(1, t).clamp_min(1e-8)).mean())
+    loss.backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+
+
 def test_pmf_rejects_bad_sizes_and_cpu(dev):
     m, _ = _model(dev)
     with pytest.raises(AssertionError, match="invalid input size"):
