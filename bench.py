@@ -185,6 +185,9 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py (our arm) needs a B200; there is no CPU fallback"
+    if world > 1:  # a rank that stops making progress must fail loudly with its stack, never hang the node
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("PMFB_BENCH_WATCHDOG", "420")), exit=True)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -196,7 +199,9 @@ def run_ours(args):
     model.train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])  # tasks/pmf/trainer.py:38-39
+        # tasks/pmf/trainer.py:38-39, plus gradient_as_bucket_view: the 372 parameter gradients are reduced in place in
+        # DDP's buckets instead of being copied in and out by ~750 tiny kernels per step
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
     opt_a, opt_b = make_optimizers(list(model.lidar_stream.parameters()),
                                    list(model.camera_stream_encoder.parameters()) + list(model.camera_stream_decoder.parameters()))
     # frame-parallel sharding: every rank owns its own B frames (weak scaling), no data-path collective
@@ -256,17 +261,19 @@ def run_ours(args):
     frames = B * world * args.steps
     value = frames / (ms * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
     # ---- roofline of the dominant kernel: the tcgen05 implicit-GEMM conv (forward + dgrad launches), timed live with
-    # CUDA events around every launch of one extra step on the launching stream.
+    # CUDA events around every launch of one extra step on the launching stream.  EVERY rank runs the instrumented
+    # steps (they go through DDP's gradient all-reduce); only rank 0 reports.
     peak_tf, peak_bw, peak_src = peaks()
     roof = None
     if args.kernel_timing:
         roof = kernel_roofline(lambda: step(d_feat, d_label), dev, ms / args.steps, peak_tf, peak_src)
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -291,6 +298,7 @@ def run_ours(args):
             "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
