@@ -30,6 +30,7 @@ import torch  # noqa: E402
 FWD_KFLOP_PER_PX = 1806.6   # PMF-ResNet34 forward, 2*MAC, convs only
 STEP_KFLOP_PER_PX = 5400.7  # forward + dgrad + wgrad (minus the two input dgrads)
 METRIC = "frames/sec PMF-ResNet34 fwd+bwd (480x640 camera grid, batch 8/GPU)"
+NCU_HALO_DRAM_BYTES_PER_LAUNCH = (38.85e9 + 22.47e9) / 199  # see kernel_roofline()
 
 
 def parse():
@@ -44,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-timing", type=int, default=1, help="extra instrumented step for the roofline object")
+    ap.add_argument("--extras", type=int, default=1, help="also time the eval forward + KNN tail (rank 0)")
     return ap.parse_args()
 
 
@@ -220,12 +222,37 @@ def run_ours(args):
         opt_b.step()
         return loss
 
+    # e2e input path: every step's frames + labels are copied from pinned host memory into one of two device buffers on
+    # a copy stream, one step ahead of the compute stream (what a DataLoader with pin_memory + non_blocking gives the
+    # trainer); the H2D of step i+1 overlaps the kernels of step i.  Every step still pays its own H2D and D2H.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(d_feat), torch.empty_like(d_label)) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]   # H2D into buffer k finished
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]  # the step reading buffer k finished
+    state = {"k": 0, "primed": False}
+
+    def prefetch(k):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[k])
+            bufs[k][0].copy_(h_feat, non_blocking=True)
+            bufs[k][1].copy_(h_label, non_blocking=True)
+            ready[k].record(copy_stream)
+
     def step_e2e():
-        x = h_feat.to(dev, non_blocking=True)
-        y = h_label.to(dev, non_blocking=True)
-        loss = step(x, y)
+        cur = torch.cuda.current_stream()
+        if not state["primed"]:
+            for k in range(2):
+                consumed[k].record(cur)
+            prefetch(0)
+            state["primed"] = True
+        k = state["k"]
+        prefetch(1 - k)                 # next step's inputs, overlapping this step's compute
+        cur.wait_event(ready[k])
+        loss = step(bufs[k][0], bufs[k][1])
+        consumed[k].record(cur)
+        state["k"] = 1 - k
         h_loss.copy_(loss.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the user reads the loss every iteration (trainer.py:384-407)
+        cur.synchronize()  # the user reads the loss every iteration (trainer.py:384-407)
         return float(h_loss)
 
     def timed(fn, k):
@@ -274,6 +301,9 @@ def run_ours(args):
             dist.barrier()
             dist.destroy_process_group()
         return
+    extras = None
+    if args.extras:
+        extras = inference_extras(model, d_feat, dev, B, H, W)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -295,11 +325,59 @@ def run_ours(args):
                     "h2d_bytes_per_step": h_feat.numel() * 4 + h_label.numel() * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "step_tflops": STEP_KFLOP_PER_PX * 1e3 * px * B / (ms / args.steps * 1e-3) / 1e12,
-            "roofline": roof, "cpu_baseline": cpu}
+            "roofline": roof, "cpu_baseline": cpu, "extras": extras}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def inference_extras(model, d_feat, dev, B, H, W):
+    """BASELINE config 5 shape of work on the PMF model: eval-mode forward (CUDA-graph replay) -> argmax -> KNN
+    back-projection (pc_processor/postproc/knn.py call signature, un-batched per frame, k=5, S=5) of P = 32768 points per
+    frame.  Reported next to the headline; rank 0 only, no collectives."""
+    import contextlib
+    import io
+
+    import pmf_b200
+    from tests import synth
+    was_training = model.training
+    model.eval()
+    with contextlib.redirect_stdout(io.StringIO()):  # the reference's ctor banner (knn.py:40-53)
+        knn = pmf_b200.KNN(dict(knn=5, search=5, sigma=1.0, cutoff=1.0), 20)
+    case = dict(name="bench", H=H, W=W, P=32768, knn=5, search=5, sigma=1.0, cutoff=1.0, nclasses=20, empty=0.9, seed=5, kind="rand")
+    inp = synth.knn_inputs(case)
+    pr, ur, px, py = (torch.from_numpy(inp[k]).to(dev) for k in ("proj_range", "unproj_range", "px", "py"))
+
+    def fwd():
+        with torch.no_grad():
+            return model(d_feat[:, 0:5], d_feat[:, 5:8])
+
+    def tail(lid):
+        am = lid.argmax(1)
+        return [knn(pr, ur, am[b], px, py) for b in range(B)]
+
+    def ev_time(fn, reps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, out
+
+    for _ in range(3):
+        lid, _cam = fwd()
+        tail(lid)
+    ms_fwd, (lid, _cam) = ev_time(fwd, 5)
+    ms_tail, _ = ev_time(lambda: tail(lid), 5)
+    model.train(was_training)
+    return {"workload": "PMF-ResNet34 eval forward (batch %d, %dx%d) + argmax + KNN(k=5,S=5) of 32768 points/frame" % (B, H, W),
+            "infer_fwd_frames_per_s": B / (ms_fwd * 1e-3), "infer_fwd_ms": ms_fwd,
+            "knn_tail_ms_per_frame": ms_tail / B, "knn_points_per_s": B * 32768 / (ms_tail * 1e-3),
+            "infer_plus_knn_frames_per_s": B / ((ms_fwd + ms_tail) * 1e-3),
+            "fwd_tflops": FWD_KFLOP_PER_PX * 1e3 * H * W * B / (ms_fwd * 1e-3) / 1e12}
 
 
 def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
@@ -418,10 +496,14 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
     dom = out.get("pmfb_conv_fwd")
     if not dom:
         return None
-    return {"bound": "tensor", "kernel": "conv_fwd_tc_kernel (tcgen05 kind::tf32 implicit GEMM: forward + dgrad launches)",
+    return {"bound": "tensor", "kernel": "conv_fwd_halo_kernel / conv_fwd_tc_kernel (tcgen05 kind::tf32 implicit GEMM: forward + dgrad launches)",
             "achieved": dom["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": dom["tflops"] / peak_tf,
             "peak_source": peak_src + "; kind::tf32 issues at half the bf16 rate, so 0.5 is this kernel's ceiling",
-            "traffic": None, "launches_per_step": dom["launches"], "ms_in_kernel_per_step": dom["ms"],
+            # DRAM bytes per launch of this kernel: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 199
+            # conv_fwd_halo_kernel launches of one step (profiles/r1_launches_step_b8_480x640_final.csv: 38.85 GB read +
+            # 22.47 GB written) / 199; the algorithmic figure of the same launches is `alg_bytes_per_launch`.
+            "traffic": NCU_HALO_DRAM_BYTES_PER_LAUNCH, "alg_bytes_per_launch": by["pmfb_conv_fwd"][3] / max(dom["launches"], 1),
+            "launches_per_step": dom["launches"], "ms_in_kernel_per_step": dom["ms"],
             "share_of_step": dom["ms"] / max(in_kernels, 1e-9),
             "wgrad": out.get("pmfb_conv_wgrad"), "cabi_ms_per_step": in_kernels,
             "eager_step_ms": e_a.elapsed_time(e_b), "breakdown": breakdown, "top_conv_launches": top}

@@ -194,6 +194,22 @@ int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view
 /* out[i*C + c] (+)= sum over pixels (per image if per_image) of x; double accumulators, caller zeroes. */
 int pmfb_colsum(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t per_image, double* out,
                 void* stream);
+/* Batched weight layout jobs: ONE launch performs pmfb_pack_weight (unpack = 0: src = OIHW weight, dst = forward
+ * packing or NULL, dst2 = dgrad packing or NULL) or pmfb_unpack_wgrad (unpack = 1: src = packed gradient, dst = OIHW
+ * gradient, dst2 unused) for every job of a DEVICE-resident table.  job.start is the exclusive prefix sum of the jobs'
+ * work sizes (pack: taps*c_out_p*c_in_p, unpack: c_out*c_in*kh*kw); total_work is the grand total.  Replaces the
+ * per-layer calls of the reference-shaped module tree (one nn.Conv2d each: salsanext.py:12-61, pmf_net.py:13-29,
+ * torchvision resnet) inside a captured training step. */
+typedef struct {
+  const float* src;
+  float* dst;
+  float* dst2;
+  int32_t c_out, c_in, kh, kw, stem, c_out_p, c_in_p, accumulate;
+  int64_t start;
+} pmfb_weight_job;
+int pmfb_weight_jobs(int32_t unpack, const pmfb_weight_job* jobs_device, int32_t n_jobs, int64_t total_work,
+                     void* stream);
+
 /* float dst = (or +=) (float)src * scale, n elements, optionally tf32-rounded. */
 int pmfb_d2f(const double* src, float* dst, int64_t n, float scale, int32_t accumulate, int32_t round_out,
              void* stream);

@@ -46,6 +46,11 @@ class WgradDesc(C.Structure):
                 ("ptile_h", i32), ("n_tile", i32), ("ksplit", i32), ("dw", C.c_void_p)]
 
 
+class WeightJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst2", C.c_void_p), ("c_out", i32), ("c_in", i32), ("kh", i32),
+                ("kw", i32), ("stem", i32), ("c_out_p", i32), ("c_in_p", i32), ("accumulate", i32), ("start", i64)]
+
+
 VP = C.POINTER(View)
 vp = C.c_void_p
 
@@ -60,6 +65,7 @@ _SIGNATURES = {
     "pmfb_nhwc_to_nchw": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
     "pmfb_pack_weight": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp], C.c_int),
     "pmfb_unpack_wgrad": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp], C.c_int),
+    "pmfb_weight_jobs": ([i32, vp, i32, i64, vp], C.c_int),
     "pmfb_pointwise": ([VP, vp, i64, i64, i64, i32, i32, i32, i32, C.POINTER(Epilogue), vp], C.c_int),
     "pmfb_bn_stats": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
     "pmfb_bn_finalize": ([vp, i64, i32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp], C.c_int),

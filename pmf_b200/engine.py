@@ -17,7 +17,7 @@ import math
 import torch
 
 from . import _lib as L
-from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ConvDesc, Epilogue, TmaSrc, View, WgradDesc
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ConvDesc, Epilogue, TmaSrc, View, WeightJob, WgradDesc
 
 BN_EPS_DEFAULT = 1e-5
 N_SM = 148
@@ -197,6 +197,13 @@ def _pick_tile(h, w, total):
     return best[1], best[2]
 
 
+def _job_table(jobs, device):
+    """ctypes WeightJob list -> device-resident table (uint8 tensor).  Built OUTSIDE graph capture (synchronous copy)."""
+    arr = (WeightJob * len(jobs))(*jobs)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device)
+
+
 class WeightCache:
     """Packed tf32 copies of the conv weights.  Eager mode: re-packed when the parameter's version or storage changes.
     Graph mode (``always=True``): packed once per pass (``begin_pass``) unconditionally, so that the pack kernels are
@@ -206,9 +213,47 @@ class WeightCache:
         self.entries = {}
         self.always = always
         self.epoch = 0
+        self.table = None
 
     def begin_pass(self):
         self.epoch += 1
+
+    # ---- graph mode: every weight of the network packed by ONE launch per pass (pmfb_weight_jobs)
+    def build_table(self, params, need_dgrad, device):
+        """Allocate the packed buffers of every nn.Conv2d under ``params`` and the device job table that packs them."""
+        convs = [params.conv(n) for n, m in params.mods.items() if isinstance(m, torch.nn.Conv2d)]
+        if not convs or any(not cp.weight.is_contiguous() for cp in convs):
+            self.table = None
+            return
+        jobs, start = [], 0
+        for cp in convs:
+            size = cp.taps * cp.c_out_p * cp.c_in_p
+            e = {"fwd": torch.empty(size, device=device, dtype=torch.float32),
+                 "dgrad": torch.empty(size, device=device, dtype=torch.float32) if need_dgrad else None,
+                 "bias": None, "tag": None}
+            self.entries[cp.name] = e
+            j = WeightJob()
+            j.src, j.dst, j.dst2 = cp.weight.data_ptr(), e["fwd"].data_ptr(), _p(e["dgrad"])
+            j.c_out, j.c_in, j.kh, j.kw, j.stem = cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0
+            j.c_out_p, j.c_in_p, j.accumulate, j.start = cp.c_out_p, cp.c_in_p, 0, start
+            jobs.append(j)
+            start += size
+        self.table = (_job_table(jobs, device), len(jobs), start, convs, need_dgrad)
+
+    def pack_all(self, stream):
+        tab, n, total, convs, need_dgrad = self.table
+        L.call("pmfb_weight_jobs", 0, tab.data_ptr(), n, total, stream)
+        tag = ("epoch", self.epoch)
+        for cp in convs:
+            e = self.entries[cp.name]
+            if cp.bias is not None:
+                if cp.c_out_p != cp.c_out:
+                    b = torch.zeros(cp.c_out_p, device=tab.device, dtype=torch.float32)
+                    b[:cp.c_out] = cp.bias.detach()
+                    e["bias"] = b
+                else:
+                    e["bias"] = cp.bias.detach()
+            e["tag"] = tag
 
     def get(self, cp, need_dgrad, stream):
         w = cp.weight
@@ -285,6 +330,12 @@ class Engine:
         self.cache = cache
         self.cache.begin_pass()
         self.st = torch.cuda.current_stream(device).cuda_stream
+        if self.cache.always and self.cache.table is not None:
+            self.cache.pack_all(self.st)
+        self._wg_list = []       # recorded convs in forward order (backward: one arena, one memset, one unpack launch)
+        self._wg_arena = None
+        self._wg_off = {}
+        self._unpack_table = None
         self.tape = []
         self.dropout = dropout  # see mask_for
         self.d64 = _Scratch(torch.float64, 1 << 17, device, self.st, zero=True)
@@ -400,7 +451,30 @@ class Engine:
             ow = (w + 2 * cp.pad - cp.dil * (cp.kw - 1) - 1) // cp.stride + 1
         assert tuple(out_t.shape) == (n, oh, ow, cp.c_out_p), (cp.name, tuple(out_t.shape), (n, oh, ow, cp.c_out_p))
         self._conv_launch(x.t, cp.c_in_p, cp.stride == 2, e["fwd"], cp.c_out_p, cp.fwd_taps(), n, oh, ow, out_t, epi)
+        if self.record:
+            self._wg_list.append(cp)
         return e
+
+    def prepare_backward(self):
+        """Graph mode, called once BEFORE the backward capture: one arena for every packed weight gradient (zeroed by a
+        single memset per pass) and the device job table that unpacks all of them into the flat gradient buffer."""
+        if self.flat_views is None or not self._wg_list:
+            return
+        jobs, off, start = [], 0, 0
+        total = sum(cp.taps * cp.c_in_p * cp.c_out_p for cp in self._wg_list)
+        self._wg_arena = torch.empty(total, device=self.device, dtype=torch.float32)
+        for cp in self._wg_list:
+            size = cp.taps * cp.c_in_p * cp.c_out_p
+            self._wg_off[cp.name] = (off, size)
+            gw = self.flat_views[cp.name + ".weight"]
+            j = WeightJob()
+            j.src, j.dst, j.dst2 = self._wg_arena.data_ptr() + 4 * off, gw.data_ptr(), None
+            j.c_out, j.c_in, j.kh, j.kw, j.stem = cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0
+            j.c_out_p, j.c_in_p, j.accumulate, j.start = cp.c_out_p, cp.c_in_p, 0, start
+            jobs.append(j)
+            off += size
+            start += cp.c_out * cp.c_in * cp.kh * cp.kw
+        self._unpack_table = (_job_table(jobs, self.device), len(jobs), start)
 
     def _conv_bwd(self, x, cp, d_pre):
         """wgrad (+ dgrad into x's gradient) of out = conv(x) given d_pre = dL/d(conv output), tf32-rounded."""
@@ -409,8 +483,13 @@ class Engine:
         _, oh, ow, co = d_pre.shape
         assert co == cp.c_out_p
         # ---- wgrad -> packed [taps][c_in_p][c_out_p] (split-K atomics; buffer zeroed here) -> OIHW
-        packed = torch.empty(cp.taps * cp.c_in_p * cp.c_out_p, device=self.device, dtype=torch.float32)
-        L.call("pmfb_memset_zero", packed.data_ptr(), packed.numel() * 4, self.st)
+        batched = self._wg_arena is not None and cp.name in self._wg_off
+        if batched:
+            off, size = self._wg_off[cp.name]
+            packed = self._wg_arena[off:off + size]
+        else:
+            packed = torch.empty(cp.taps * cp.c_in_p * cp.c_out_p, device=self.device, dtype=torch.float32)
+            L.call("pmfb_memset_zero", packed.data_ptr(), packed.numel() * 4, self.st)
         d = WgradDesc()
         d.x = self._tma_src(x.t, cp.c_in_p, cp.stride == 2)
         d.dy = self._tma_src(d_pre, cp.c_out_p)
@@ -426,8 +505,9 @@ class Engine:
         d.dw = packed.data_ptr()
         L.call("pmfb_conv_wgrad", C.byref(d), self.st)
         gw = self._pgrad(cp.name + ".weight", cp.weight)
-        L.call("pmfb_unpack_wgrad", packed.data_ptr(), cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0, cp.c_out_p,
-               cp.c_in_p, gw.data_ptr(), 0, self.st)
+        if not batched:
+            L.call("pmfb_unpack_wgrad", packed.data_ptr(), cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0, cp.c_out_p,
+                   cp.c_in_p, gw.data_ptr(), 0, self.st)
         self.param_grads[cp.name + ".weight"] = gw
         # ---- dgrad
         if not x.needs_grad:
@@ -756,7 +836,12 @@ class Engine:
         self.st = torch.cuda.current_stream(self.device).cuda_stream
         self.d64 = _Scratch(torch.float64, 1 << 17, self.device, self.st, zero=True)
         self.f32.stream = self.st
+        if self._wg_arena is not None:
+            L.call("pmfb_memset_zero", self._wg_arena.data_ptr(), self._wg_arena.numel() * 4, self.st)
         for fn in reversed(self.tape):
             fn()
+        if self._unpack_table is not None:
+            tab, n, total = self._unpack_table
+            L.call("pmfb_weight_jobs", 1, tab.data_ptr(), n, total, self.st)
         self.tape = []
         return self.param_grads

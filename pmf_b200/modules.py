@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import net as G
+from . import _lib as _L
 from .engine import Act, Engine, WeightCache
 
 
@@ -302,11 +303,16 @@ class _GraphedPMF:
         self.img7 = self.E_in.new(n, h, w, 32, needs_grad=False)
         self.pcd = self.E_in.new(n, h, w, (c_pcd + 3) // 4 * 4, needs_grad=False)
         self._stage_inputs(pcd, img)
+        self.cache.build_table(G.ModuleParams(mod), record, self.dev)  # every weight packed by one launch per pass
         torch.cuda.synchronize(self.dev)
+        l0 = _L.launches
         with torch.cuda.graph(self.g_fwd, pool=self.pool, capture_error_mode="thread_local"):  # NCCL watchdog threads may poll events
             E = Engine(G.ModuleParams(mod), self.dev, mod.training, record, self.cache, dropout=mod._dropout_masks())
             self.lidar, self.camera, self.ll, self.cl = G.pmf_forward_packed(E, self.pcd, self.img7, mod.image_backbone,
                                                                              mod.nclasses)
+        self.n_fwd_calls = _L.launches - l0  # C-ABI launches one replay of the forward graph stands for
+        _L.launches = l0                     # capturing enqueues nothing
+        self.n_bwd_calls = 0
         self.E = E
         self.ll_grad = self.cl_grad = None
         # all parameter gradients live in ONE flat buffer: a single clone per step hands them to autograd
@@ -326,6 +332,7 @@ class _GraphedPMF:
     def forward(self, pcd, img):
         self._stage_inputs(pcd, img)
         self.g_fwd.replay()
+        _L.launches += self.n_fwd_calls
         self.version += 1
         return self.lidar.clone(), self.camera.clone()
 
@@ -338,11 +345,16 @@ class _GraphedPMF:
         E.softmax_backward_into(self.ll_grad, self.lidar, d_lidar, stream=st)
         E.softmax_backward_into(self.cl_grad, self.camera, d_camera, stream=st)
         if not self.bwd_captured:
+            E.prepare_backward()
             torch.cuda.synchronize(self.dev)
+            l0 = _L.launches
             with torch.cuda.graph(self.g_bwd, pool=self.pool, capture_error_mode="thread_local"):
                 self.grads = E.run_backward()
+            self.n_bwd_calls = _L.launches - l0
+            _L.launches = l0
             self.bwd_captured = True
         self.g_bwd.replay()
+        _L.launches += self.n_bwd_calls
         out = self.flat.clone()
         return tuple(out[o:o + k].view(shp) if nm in self.grads else None
                      for nm, (o, k, shp) in ((nm, self.offs[nm]) for nm in self.names))
