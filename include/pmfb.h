@@ -194,6 +194,20 @@ int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view
 /* out[i*C + c] (+)= sum over pixels (per image if per_image) of x; double accumulators, caller zeroes. */
 int pmfb_colsum(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t per_image, double* out,
                 void* stream);
+/* EPMF sparse-conv mask ops (pc_processor/models/epmf_net.py).
+ * pmfb_pixel_mask:   mask[n,y,x] = (sum_c |x[n,y,x,c]| != 0) ? 1 : 0                      (epmf_net.py:67)
+ * pmfb_mask_maxpool: mask_out = MaxPool2d(k, stride, padding=0, dilation)(F.pad(mask_in, pad)), dense (N,H,W) fp32 maps,
+ *                    output (h + 2 pad - dilation (k-1) - 1) / stride + 1 per side                 (epmf_net.py:43-44)
+ * pmfb_pixel_scale:  out = (act(in * pre_mask[p]) * alpha[c] + beta[c] + r) * post_mask[p], optional tf32 rounding;
+ *                    NULL pointers skip a step: the x*mask / LeakyReLU / eval BatchNorm / +shortcut / *mask chain
+ *                    around SparseVariantConv                                                      (epmf_net.py:31,49,69-82) */
+int pmfb_pixel_mask(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, float* mask, void* stream);
+int pmfb_mask_maxpool(const float* mask_in, int32_t n, int32_t h, int32_t w, int32_t k, int32_t stride, int32_t dilation,
+                      int32_t pad, float* mask_out, void* stream);
+int pmfb_pixel_scale(const pmfb_view* in, int32_t n, int32_t h, int32_t w, int32_t c, const float* pre_mask, int32_t act,
+                     const float* alpha, const float* beta, const pmfb_view* r, const float* post_mask, float* out,
+                     int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t round_out, void* stream);
+
 /* Batched weight layout jobs: ONE launch performs pmfb_pack_weight (unpack = 0: src = OIHW weight, dst = forward
  * packing or NULL, dst2 = dgrad packing or NULL) or pmfb_unpack_wgrad (unpack = 1: src = packed gradient, dst = OIHW
  * gradient, dst2 unused) for every job of a DEVICE-resident table.  job.start is the exclusive prefix sum of the jobs'

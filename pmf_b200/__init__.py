@@ -2,9 +2,10 @@
 
 Public surface (mirrors the reference's names):
     pmf_b200.PMFNet, pmf_b200.ResidualBasedFusionBlock      pc_processor/models/pmf_net.py
+    pmf_b200.EPMFNet (inference only)                       pc_processor/models/epmf_net.py
     pmf_b200.KNN                                            pc_processor/postproc/knn.py
     pmf_b200.project_scatter                                perspective projection (parser.py:209-227 + loader scatter)
 Everything computes through libpmf_b200.so (include/pmfb.h); there is no CPU path.
 """
-from .modules import PMFNet, ResidualBasedFusionBlock  # noqa: F401
+from .modules import EPMFNet, PMFNet, ResidualBasedFusionBlock  # noqa: F401
 from .postproc import KNN, project_scatter  # noqa: F401

@@ -66,6 +66,9 @@ _SIGNATURES = {
     "pmfb_pack_weight": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp], C.c_int),
     "pmfb_unpack_wgrad": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp], C.c_int),
     "pmfb_weight_jobs": ([i32, vp, i32, i64, vp], C.c_int),
+    "pmfb_pixel_mask": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
+    "pmfb_mask_maxpool": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, vp], C.c_int),
+    "pmfb_pixel_scale": ([VP, i32, i32, i32, i32, vp, i32, vp, vp, VP, vp, vp, i64, i64, i64, i32, vp], C.c_int),
     "pmfb_pointwise": ([VP, vp, i64, i64, i64, i32, i32, i32, i32, C.POINTER(Epilogue), vp], C.c_int),
     "pmfb_bn_stats": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
     "pmfb_bn_finalize": ([vp, i64, i32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp], C.c_int),

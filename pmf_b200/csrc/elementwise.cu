@@ -730,6 +730,125 @@ extern "C" int pmfb_unpack_wgrad(const float* packed, int32_t c_out, int32_t c_i
   return PMFB_OK;
 }
 
+// ------------------------------------------------------------------------------------ EPMF sparse-conv mask ops
+// epmf_net.py:67  mask = x.abs().sum(1).ne(0)            -> pixel_mask_kernel
+// epmf_net.py:43  mask = MaxPool2d(k, stride, 0, dil)(F.pad(mask, pad))  (zero padding)  -> mask_maxpool_kernel
+// epmf_net.py:31,49,69-82  x*mask, LeakyReLU, BatchNorm (eval affine), +shortcut, *mask  -> pixel_scale_kernel
+namespace pmfb {
+
+__global__ void __launch_bounds__(256)
+pixel_mask_kernel(EpiView x, int n, int h, int w, int c4, float* __restrict__ mask) {
+  const long long total = (long long)n * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long p = i;
+    const int xx = (int)(p % w);
+    p /= w;
+    const int yy = (int)(p % h);
+    const int ni = (int)(p / h);
+    const float* s = x.p + (long long)ni * x.sn + (long long)yy * x.sy + (long long)xx * x.sx;
+    float acc = 0.f;
+    for (int g = 0; g < c4; ++g) {
+      const float4 v = ld4(s + 4 * g);
+      acc += fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w);
+    }
+    mask[i] = acc != 0.f ? 1.f : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mask_maxpool_kernel(const float* __restrict__ in, int n, int h, int w, int k, int stride, int dil, int pad, int oh, int ow,
+                    float* __restrict__ out) {
+  const long long total = (long long)n * oh * ow;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long p = i;
+    const int ox = (int)(p % ow);
+    p /= ow;
+    const int oy = (int)(p % oh);
+    const int ni = (int)(p / oh);
+    float m = 0.f;  // the zero padding takes part in the maximum; masks are >= 0
+    bool any = false;
+    for (int a = 0; a < k; ++a) {
+      const int yy = oy * stride - pad + a * dil;
+      for (int b = 0; b < k; ++b) {
+        const int xx = ox * stride - pad + b * dil;
+        const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? in[((long long)ni * h + yy) * w + xx] : 0.f;
+        m = any ? fmaxf(m, v) : v;
+        any = true;
+      }
+    }
+    out[i] = m;
+  }
+}
+
+// out = (act(in * pre[p]) * alpha[c] + beta[c] + r) * post[p], optional tf32 rounding; thread = (pixel, float4 group)
+__global__ void __launch_bounds__(256)
+pixel_scale_kernel(EpiView in, int n, int h, int w, int c4, const float* __restrict__ pre, int act, const float* __restrict__ alpha,
+                   const float* __restrict__ beta, EpiView r, const float* __restrict__ post, float* out, long long o_sn,
+                   long long o_sy, long long o_sx, int round_out) {
+  const long long total = (long long)n * h * w * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % c4);
+    long long p = i / c4;
+    const long long pix = p;
+    const int xx = (int)(p % w);
+    p /= w;
+    const int yy = (int)(p % h);
+    const int ni = (int)(p / h);
+    const int c = 4 * g;
+    float4 v = ld4(in.p + (long long)ni * in.sn + (long long)yy * in.sy + (long long)xx * in.sx + c);
+    if (pre) { const float m = pre[pix]; v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
+    if (act) { v.x = epi_act(act, v.x); v.y = epi_act(act, v.y); v.z = epi_act(act, v.z); v.w = epi_act(act, v.w); }
+    if (alpha) { const float4 a = ld4(alpha + c); v.x *= a.x; v.y *= a.y; v.z *= a.z; v.w *= a.w; }
+    if (beta) { const float4 b = ld4(beta + c); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+    if (r.p) {
+      const float4 q = ld4(r.p + (long long)ni * r.sn + (long long)yy * r.sy + (long long)xx * r.sx + c);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    if (post) { const float m = post[pix]; v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
+    if (round_out) v = rnd4(v);
+    *reinterpret_cast<float4*>(out + (long long)ni * o_sn + (long long)yy * o_sy + (long long)xx * o_sx + c) = v;
+  }
+}
+
+}  // namespace pmfb
+
+extern "C" int pmfb_pixel_mask(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, float* mask, void* stream) {
+  REQ(x && x->ptr && view_ok(x) && mask && c > 0 && c % 4 == 0, "pixel_mask: bad arguments (c=%d)", c);
+  const long long total = (long long)n * h * w;
+  if (total == 0) return PMFB_OK;
+  pixel_mask_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(x), n, h, w, c / 4, mask);
+  PMFB_LAUNCH_CHECK("pixel_mask_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_mask_maxpool(const float* mask_in, int32_t n, int32_t h, int32_t w, int32_t k, int32_t stride, int32_t dilation,
+                                 int32_t pad, float* mask_out, void* stream) {
+  REQ(mask_in && mask_out && k >= 1 && stride >= 1 && dilation >= 1 && pad >= 0, "mask_maxpool: bad arguments");
+  const int oh = (h + 2 * pad - dilation * (k - 1) - 1) / stride + 1, ow = (w + 2 * pad - dilation * (k - 1) - 1) / stride + 1;
+  REQ(oh > 0 && ow > 0, "mask_maxpool: empty output");
+  const long long total = (long long)n * oh * ow;
+  if (total == 0) return PMFB_OK;
+  mask_maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mask_in, n, h, w, k, stride, dilation, pad, oh, ow,
+                                                                              mask_out);
+  PMFB_LAUNCH_CHECK("mask_maxpool_kernel");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_pixel_scale(const pmfb_view* in, int32_t n, int32_t h, int32_t w, int32_t c, const float* pre_mask, int32_t act,
+                                const float* alpha, const float* beta, const pmfb_view* r, const float* post_mask, float* out,
+                                int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t round_out, void* stream) {
+  REQ(in && in->ptr && view_ok(in) && out_ok(out, o_sn, o_sy, o_sx) && c > 0 && c % 4 == 0, "pixel_scale: bad arguments (c=%d)", c);
+  REQ(!r || view_ok(r), "pixel_scale: bad residual view");
+  REQ(act >= 0 && act <= 3, "pixel_scale: act=%d", act);
+  const long long total = (long long)n * h * w * (c / 4);
+  if (total == 0) return PMFB_OK;
+  pixel_scale_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(in), n, h, w, c / 4, pre_mask, act, alpha, beta,
+                                                                             r ? ev(r) : ev(nullptr), post_mask, out, o_sn, o_sy,
+                                                                             o_sx, round_out);
+  PMFB_LAUNCH_CHECK("pixel_scale_kernel");
+  return PMFB_OK;
+}
+
 // ------------------------------------------------------------------------------------ batched weight jobs
 // One launch packs (or unpacks) EVERY convolution weight of the network: a device-resident table of jobs, each owning
 // the global work range [start, next start).  A training step issued 110 pack + 110 unpack + 110 memset launches of a

@@ -706,6 +706,63 @@ class Engine:
             self.tape.append(bwd)
         return y
 
+    # ------------------------------------------------------------------------------------------ EPMF sparse-conv ops (eval)
+    def pixel_mask(self, x):
+        """(N,H,W) fp32 map: 1 where any channel of the pixel is non-zero (epmf_net.py:67)."""
+        n, h, w, c = x.shape
+        m = torch.empty((n, h, w), device=self.device, dtype=torch.float32)
+        L.call("pmfb_pixel_mask", C.byref(_view(x.t)), n, h, w, c, m.data_ptr(), self.st)
+        return m
+
+    def mask_maxpool(self, m, k, stride, dil, pad):
+        """MaxPool2d(k, stride, 0, dil)(F.pad(m, pad)) of a pixel mask (epmf_net.py:43-44)."""
+        n, h, w = m.shape
+        oh = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        ow = (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        out = torch.empty((n, oh, ow), device=self.device, dtype=torch.float32)
+        L.call("pmfb_mask_maxpool", m.data_ptr(), n, h, w, k, stride, dil, pad, out.data_ptr(), self.st)
+        return out
+
+    def sparse_conv(self, x, mask, name):
+        """SparseVariantConv (epmf_net.py:10-50) up to, not including, the final ``* mask``: returns
+        (conv(x) + conv.bias + bias  [NHWC tensor, NOT yet masked],  dilated mask).  The caller guarantees x == x*mask
+        (true whenever x was produced with ``post=mask`` or the mask was derived from x itself)."""
+        if self.record:
+            raise NotImplementedError("pmf_b200: the EPMF sparse convolution has no backward yet (inference only)")
+        cp = self.P.conv(name + ".conv")
+        extra = self.P.mods[name.lstrip(".")].bias
+        e = self.cache.get(cp, False, self.st)
+        bias = e["bias"]
+        if extra is not None:
+            b2 = self.f32.take(cp.c_out_p)
+            src = bias if bias is not None else torch.zeros(cp.c_out_p, device=self.device)
+            ex = extra.detach()
+            if cp.c_out_p != cp.c_out:
+                exp = torch.zeros(cp.c_out_p, device=self.device, dtype=torch.float32)
+                exp[:cp.c_out] = ex
+                ex = exp
+            self.pointwise(src.view(1, 1, 1, -1), b2.view(1, 1, 1, -1), r1=ex.view(1, 1, 1, -1))
+            bias = b2
+        n, h, w, _ = x.shape
+        oh = (h + 2 * cp.pad - cp.dil * (cp.kh - 1) - 1) // cp.stride + 1
+        ow = (w + 2 * cp.pad - cp.dil * (cp.kw - 1) - 1) // cp.stride + 1
+        y = torch.empty((n, oh, ow, cp.c_out_p), device=self.device, dtype=torch.float32)
+        self._conv_fwd(x, cp, y, self._epi(beta1=bias))
+        return y, self.mask_maxpool(mask, cp.kh, cp.stride, cp.dil, cp.pad)
+
+    def pixel_scale(self, src_t, out=None, pre=None, act=ACT_NONE, bn=None, r=None, post=None, rnd=True):
+        """out = (BN_eval(act(src * pre[pixel])) + r) * post[pixel]  (epmf_net.py:31,49,69-82)."""
+        n, h, w, c = src_t.shape
+        if out is None:
+            out = self.new(n, h, w, c, needs_grad=False)
+        alpha = beta = None
+        if bn is not None:
+            alpha, beta = self._bn_eval_affine(self.P.bn(bn))
+        rv = _view(r.t) if r is not None else View()
+        L.call("pmfb_pixel_scale", C.byref(_view(src_t)), n, h, w, c, _p(pre), act, _p(alpha), _p(beta), C.byref(rv), _p(post),
+               out.t.data_ptr(), out.t.stride(0), out.t.stride(1), out.t.stride(2), 1 if rnd else 0, self.st)
+        return out
+
     # ------------------------------------------------------------------------------------------ data movement ops
     def copy(self, src, dst, mask=None):
         """dst = src * mask (a channel slice of a concat buffer)."""

@@ -432,6 +432,175 @@ class PMFNet(nn.Module):
         return _PMFFn.apply(self, record, pcd_feature, img_feature, *params)
 
 
+# ------------------------------------------------------------------------------------------ epmf_net.py (inference)
+class SparseVariantConv(nn.Module):
+    """Parameters of epmf_net.py:10-28 (``conv`` + separate ``bias``; kaiming-normal fan_out init at :24-28)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, padding=0, stride=1, groups=1, dilation=1, bias=True):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, padding=padding, stride=stride, groups=groups,
+                              dilation=dilation)
+        self.pool = nn.MaxPool2d(kernel_size, stride=stride, padding=0, dilation=dilation)
+        self.bias = nn.Parameter(torch.zeros(out_channels).float()) if bias else None
+        nn.init.kaiming_normal_(self.conv.weight, mode="fan_out", nonlinearity="leaky_relu")
+
+
+class SparseResContextBlock(nn.Module):
+    """Parameters of epmf_net.py:52-64."""
+
+    def __init__(self, in_filters, out_filters, stride=1):
+        super().__init__()
+        self.conv1 = SparseVariantConv(in_filters, out_filters, 3, padding=1, stride=stride)
+        self.act1 = nn.LeakyReLU()
+        self.conv2 = SparseVariantConv(out_filters, out_filters, (3, 3), padding=(1, 1))
+        self.act2 = nn.LeakyReLU()
+        self.bn1 = nn.BatchNorm2d(out_filters)
+        self.conv3 = SparseVariantConv(out_filters, out_filters, (3, 3), padding=(2, 2), dilation=2)
+        self.act3 = nn.LeakyReLU()
+        self.bn2 = nn.BatchNorm2d(out_filters)
+
+
+def _conv_lrelu_bn_shuffle(cin, cout):
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.LeakyReLU(), nn.BatchNorm2d(cout), nn.PixelShuffle(2))
+
+
+class EPMFSalsaNextFusion(nn.Module):
+    """Parameters of epmf_net.py:84-102, created in the reference's order: SalsaNext.__init__ (salsanext.py:166-187,
+    including its three dense context blocks, which the subclass then REPLACES), then the sparse context blocks, the
+    fusion blocks, ASPP and extraUpSample."""
+
+    def __init__(self, in_channels=8, nclasses=20, base_channels=32, img_feature_channels=()):
+        super().__init__()
+        b = base_channels
+        self.base_channels = b
+        self.dropout_ratio = 0.2
+        self.downCntx = ResContextBlock(in_channels, b)
+        self.downCntx2 = ResContextBlock(b, b)
+        self.downCntx3 = ResContextBlock(b, b)
+        self.resBlock1 = ResBlock(b, 2 * b, self.dropout_ratio, pooling=True, drop_out=False)
+        self.resBlock2 = ResBlock(2 * b, 4 * b, self.dropout_ratio, pooling=True)
+        self.resBlock3 = ResBlock(4 * b, 8 * b, self.dropout_ratio, pooling=True)
+        self.resBlock4 = ResBlock(8 * b, 8 * b, self.dropout_ratio, pooling=True)
+        self.resBlock5 = ResBlock(8 * b, 8 * b, self.dropout_ratio, pooling=False)
+        self.upBlock1 = UpBlock(8 * b, 4 * b, self.dropout_ratio)
+        self.upBlock2 = UpBlock(4 * b, 4 * b, self.dropout_ratio)
+        self.upBlock3 = UpBlock(4 * b, 2 * b, self.dropout_ratio)
+        self.upBlock4 = UpBlock(2 * b, b, self.dropout_ratio, drop_out=False)
+        self.logits = nn.Conv2d(b, nclasses, kernel_size=(1, 1))
+        self.softmax = True
+        self.downCntx = SparseResContextBlock(in_channels, b)
+        self.downCntx2 = SparseResContextBlock(b, b)
+        self.downCntx3 = SparseResContextBlock(b, b, stride=2)
+        self.fusionblock_1 = _FusionContainer(b, img_feature_channels[0])
+        self.fusionblock_2 = _FusionContainer(2 * b, img_feature_channels[1])
+        self.fusionblock_3 = _FusionContainer(4 * b, img_feature_channels[2])
+        self.fusionblock_4 = _FusionContainer(8 * b, img_feature_channels[3])
+        self.aspp = ASPP(8 * b, 8 * b)
+        self.extraUpSample = _conv_lrelu_bn_shuffle(b, 4 * b)
+
+
+class EPMFRGBDecoder(nn.Module):
+    """Parameters of epmf_net.py:134-173."""
+
+    def __init__(self, in_channels=(), nclasses=4, base_channels=64, lidar_base_channels=32):
+        super().__init__()
+
+        def stage(cin, k, pad):
+            return nn.Sequential(nn.Conv2d(cin, base_channels, k, padding=pad), nn.LeakyReLU(), nn.BatchNorm2d(base_channels),
+                                 nn.Upsample(scale_factor=2, mode="bilinear"))
+
+        self.aspp = ASPP(in_channels[3], in_channels[3])
+        self.extraUpSample = _conv_lrelu_bn_shuffle(lidar_base_channels * 8, lidar_base_channels * 8)
+        self.up_4a = stage(in_channels[3] + lidar_base_channels * 2, 3, 1)
+        self.up_3a = stage(in_channels[2] + base_channels, 3, 1)
+        self.up_2a = stage(in_channels[1] + base_channels, 3, 1)
+        self.up_1a = stage(in_channels[0] + base_channels, 1, 0)
+        self.conv = nn.Conv2d(base_channels, nclasses, kernel_size=3, padding=1)
+
+
+class _GraphedEPMF:
+    """One (shape, parameter-storage) specialisation of the EPMF eval forward captured into a CUDA graph."""
+
+    def __init__(self, mod, pcd, img):
+        self.dev = pcd.device
+        n, c_pcd, h, w = pcd.shape
+        self.cache = WeightCache(always=True)
+        self.pool = torch.cuda.graph_pool_handle()
+        self.g = torch.cuda.CUDAGraph()
+        self.E_in = Engine(G.ModuleParams(mod), self.dev, False, False, WeightCache(), dropout=False)
+        self.img7 = self.E_in.new(n, h, w, 32, needs_grad=False)
+        self.pcd = self.E_in.new(n, h, w, (c_pcd + 3) // 4 * 4, needs_grad=False)
+        self._stage_inputs(pcd, img)
+        self.cache.build_table(G.ModuleParams(mod), False, self.dev)
+        torch.cuda.synchronize(self.dev)
+        l0 = _L.launches
+        with torch.cuda.graph(self.g, pool=self.pool, capture_error_mode="thread_local"):
+            E = Engine(G.ModuleParams(mod), self.dev, False, False, self.cache, dropout=False)
+            self.lidar, self.camera, _, _ = G.epmf_forward_packed(E, self.pcd, self.img7, mod.image_backbone, mod.nclasses)
+        self.n_calls = _L.launches - l0
+        _L.launches = l0
+        self.E = E
+
+    def _stage_inputs(self, pcd, img):
+        self.E_in.st = torch.cuda.current_stream(self.dev).cuda_stream
+        self.E_in.input_nchw(img, 32, n_shift=7, out=self.img7)
+        self.E_in.input_nchw(pcd, self.pcd.c, out=self.pcd)
+
+    def forward(self, pcd, img):
+        self._stage_inputs(pcd, img)
+        self.g.replay()
+        _L.launches += self.n_calls
+        return self.lidar.clone(), self.camera.clone()
+
+
+class EPMFNet(nn.Module):
+    """epmf_net.py:185-216, INFERENCE ONLY in this round: forward under ``torch.no_grad()`` / ``.eval()`` returns the two
+    softmax probability maps (B, nclasses, H, W); H and W must be multiples of 32.  A forward that would have to
+    record gradients raises NotImplementedError (the sparse convolution has no backward yet)."""
+
+    def __init__(self, pcd_channels=5, img_channels=3, nclasses=20, base_channels=32, imagenet_pretrained=True,
+                 image_backbone="resnet34"):
+        super().__init__()
+        if "resnet" not in image_backbone:
+            raise NotImplementedError(image_backbone)
+        self.camera_stream_encoder = ResNet(in_channels=img_channels, pretrained=imagenet_pretrained, backbone=image_backbone)
+        self.camera_stream_decoder = EPMFRGBDecoder(self.camera_stream_encoder.feature_channels, nclasses=nclasses,
+                                                    base_channels=self.camera_stream_encoder.expansion * 16,
+                                                    lidar_base_channels=base_channels)
+        self.lidar_stream = EPMFSalsaNextFusion(in_channels=pcd_channels, nclasses=nclasses, base_channels=base_channels,
+                                                img_feature_channels=self.camera_stream_encoder.feature_channels)
+        self.nclasses = nclasses
+        self.image_backbone = image_backbone
+        self._cache = WeightCache()
+        self._graphs = {}
+        self._seen = set()
+
+    def forward(self, pcd_feature, img_feature):
+        _require_cuda(pcd_feature, img_feature)
+        if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("pmf_b200.EPMFNet is inference-only in this round: call .eval() and run the forward "
+                                      "under torch.no_grad()")
+        h, w = img_feature.shape[2], img_feature.shape[3]
+        if h % 32 != 0 or w % 32 != 0:
+            assert False, "invalid input size: {}".format(img_feature.shape)
+        use_graph = os.environ.get("PMFB_CUDA_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing()
+        if use_graph:
+            key = (tuple(pcd_feature.shape), tuple(img_feature.shape), str(pcd_feature.device),
+                   tuple(p.data_ptr() for p in self.parameters()) + tuple(b.data_ptr() for b in self.buffers()))
+            runner = self._graphs.get(key)
+            if runner is None and key in self._seen:
+                if len(self._graphs) >= 4:
+                    self._graphs.clear()
+                torch.cuda.empty_cache()
+                runner = self._graphs[key] = _GraphedEPMF(self, pcd_feature, img_feature)
+            self._seen.add(key)
+            if runner is not None:
+                return runner.forward(pcd_feature, img_feature)
+        E = Engine(G.ModuleParams(self), pcd_feature.device, False, False, self._cache, dropout=False)
+        lidar, camera, _, _ = G.epmf_forward(E, pcd_feature, img_feature, self.image_backbone, self.nclasses)
+        return lidar, camera
+
+
 class _DropoutSites(dict):
     """Lazily answers Engine.mask_for(site): draws a fresh Dropout2d scale when the site's module is training."""
 

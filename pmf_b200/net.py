@@ -190,6 +190,105 @@ def rgb_decoder(E, feats, p):
     return E.conv_act(x, p + ".conv", ACT_NONE, rnd=False)
 
 
+# ---------------------------------------------------------------------------------------------- epmf_net.py (inference)
+def sparse_context_block(E, x, p, out=None):
+    """ResContextBlock.forward of epmf_net.py:66-82 (SparseVariantConv at :30-50), eval mode.
+    x*mask is the identity for conv1 (the mask is derived from x) and conv2 (its input is LeakyReLU(y*mask))."""
+    m0 = E.pixel_mask(x)
+    s_pre, m1 = E.sparse_conv(x, m0, p + ".conv1")
+    n, h, w, c = s_pre.shape
+    s = E.pixel_scale(s_pre, pre=m1, act=ACT_LEAKY)
+    a_pre, m2 = E.sparse_conv(s, m1, p + ".conv2")
+    a1 = E.pixel_scale(a_pre, pre=m2, act=ACT_LEAKY, bn=p + ".bn1", post=m2)          # bn1(...) * mask: conv3's input
+    b_pre, m3 = E.sparse_conv(a1, m2, p + ".conv3")
+    return E.pixel_scale(b_pre, out=out, pre=m3, act=ACT_LEAKY, bn=p + ".bn2", r=s, post=m3)  # (shortcut + bn2(...)) * mask
+
+
+def conv_lrelu_bn_shuffle(E, x, p, out):
+    """nn.Sequential(Conv2d 3x3, LeakyReLU, BatchNorm2d, PixelShuffle(2)), epmf_net.py:97-102 / 138-143."""
+    y = E.conv_act_bn(x, p + ".0", p + ".2")
+    return E.pixel_shuffle(y, out)
+
+
+def epmf_salsanext_fusion(E, pcd, feats, p, nclasses):
+    """SalsaNextFusion.forward, epmf_net.py:104-131 -> (NHWC logits Act, down5c Act).  The LiDAR stream runs at half
+    resolution from downCntx3 on and each fusion block PRECEDES its ResBlock."""
+    n, h, w, _ = pcd.shape
+    b = E.P.conv(p + ".downCntx.conv1.conv").c_out
+    d = sparse_context_block(E, pcd, p + ".downCntx")
+    d = sparse_context_block(E, d, p + ".downCntx2")
+    img = feats[0]
+    cat = E.new(n, h // 2, w // 2, b + img.c, needs_grad=False)
+    sparse_context_block(E, d, p + ".downCntx3", out=cat.slice(0, b))
+    E.copy(img, cat.slice(b, b + img.c))
+    x = fusion_block(E, cat, b, p + ".fusionblock_1")
+    skips = []
+    for i in range(4):
+        rb = "%s.resBlock%d" % (p, i + 1)
+        c = E.P.conv(rb + ".conv1").c_out
+        if i < 3:
+            img = feats[i + 1]
+            cat = E.new(n, x.shape[1] // 2, x.shape[2] // 2, c + img.c, needs_grad=False)
+            _, skip = res_block(E, x, rb, pooling=True, drop_out=(i > 0), pool_out=cat.slice(0, c))
+            E.copy(img, cat.slice(c, c + img.c))
+            x = fusion_block(E, cat, c, "%s.fusionblock_%d" % (p, i + 2))
+        else:
+            x, skip = res_block(E, x, rb, pooling=True, drop_out=True)
+        skips.append(skip)
+    x = res_block(E, x, p + ".resBlock5", pooling=False)
+    d5c = aspp(E, x, p + ".aspp")
+    x = up_block(E, d5c, skips[3], p + ".upBlock1")
+    x = up_block(E, x, skips[2], p + ".upBlock2")
+    x = up_block(E, x, skips[1], p + ".upBlock3")
+    x = up_block(E, x, skips[0], p + ".upBlock4", drop_out=False)
+    up = conv_lrelu_bn_shuffle(E, x, p + ".extraUpSample", E.new(n, 2 * x.shape[1], 2 * x.shape[2], b, needs_grad=False))
+    return E.conv_act(up, p + ".logits", ACT_NONE, rnd=False), d5c
+
+
+def epmf_rgb_decoder(E, feats, lidar_feature, p):
+    """RGBDecoder.forward, epmf_net.py:175-183 -> NHWC logits Act."""
+    n = feats[0].shape[0]
+    dc = E.P.conv(p + ".up_4a.0").c_out
+    cu = E.P.conv(p + ".extraUpSample.0").c_out // 4
+    ca = E.P.conv(p + ".aspp.conv_1x1_output").c_out
+    _, hh, ww, _ = feats[3].shape
+    fuse = E.new(n, hh, ww, cu + ca, needs_grad=False)
+    conv_lrelu_bn_shuffle(E, lidar_feature, p + ".extraUpSample", fuse.slice(0, cu))
+    E.copy(aspp(E, feats[3], p + ".aspp"), fuse.slice(cu, cu + ca))
+    x = fuse
+    for name, skip in ((".up_4a", feats[2]), (".up_3a", feats[1]), (".up_2a", feats[0]), (".up_1a", None)):
+        y = E.conv_act_bn(x, p + name + ".0", p + name + ".2")
+        _, hh, ww, _ = y.shape
+        if skip is not None:
+            cat = E.new(n, 2 * hh, 2 * ww, dc + skip.c, needs_grad=False)
+            E.upsample2x(y, cat.slice(0, dc))
+            E.copy(skip, cat.slice(dc, dc + skip.c))
+            x = cat
+        else:
+            x = E.upsample2x(y, E.new(n, 2 * hh, 2 * ww, dc, needs_grad=False))
+    return E.conv_act(x, p + ".conv", ACT_NONE, rnd=False)
+
+
+def epmf_forward_packed(E, pcd, img7, backbone, nclasses):
+    """EPMFNet.forward, epmf_net.py:209-216, from the packed NHWC inputs."""
+    feats = resnet_encoder(E, img7, "camera_stream_encoder", backbone)
+    lidar_logits, lidar_feature = epmf_salsanext_fusion(E, pcd, feats, "lidar_stream", nclasses)
+    camera_logits = epmf_rgb_decoder(E, feats, lidar_feature, "camera_stream_decoder")
+    lidar = E.softmax_nchw(lidar_logits, nclasses)
+    camera = E.softmax_nchw(camera_logits, nclasses)
+    E.finish_forward()
+    return lidar, camera, lidar_logits, camera_logits
+
+
+def epmf_forward(E, pcd_feature, img_feature, backbone, nclasses):
+    h, w = img_feature.shape[2], img_feature.shape[3]
+    if h % 32 != 0 or w % 32 != 0:  # the half-resolution LiDAR stream pools four more times (SURVEY.md 8a-12)
+        assert False, "invalid input size: {}".format(img_feature.shape)
+    img7 = E.input_nchw(img_feature, 32, n_shift=7)
+    pcd = E.input_nchw(pcd_feature, (pcd_feature.shape[1] + 3) // 4 * 4)
+    return epmf_forward_packed(E, pcd, img7, backbone, nclasses)
+
+
 def check_input_size(img_feature):
     h, w = img_feature.shape[2], img_feature.shape[3]
     if h % 16 != 0 or w % 16 != 0:

@@ -419,6 +419,44 @@ def pmfb_conv_wgrad(dp_, stream):
         dw[t] += a.T @ dy
 
 
+def pmfb_pixel_mask(x, n, h, w, c, mask, stream):
+    v = _view(_deref(x), n, h, w, c)
+    _arr(mask, (n, h, w), (h * w, w, 1))[...] = (np.abs(v).sum(-1) != 0).astype(np.float32)
+
+
+def pmfb_mask_maxpool(mask_in, n, h, w, k, stride, dil, pad, mask_out, stream):
+    m = _arr(mask_in, (n, h, w), (h * w, w, 1))
+    oh = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    ow = (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    mp = np.zeros((n, h + 2 * pad, w + 2 * pad), np.float32)
+    mp[:, pad:pad + h, pad:pad + w] = m
+    out = None
+    for a in range(k):
+        for b in range(k):
+            t = mp[:, a * dil:a * dil + (oh - 1) * stride + 1:stride, b * dil:b * dil + (ow - 1) * stride + 1:stride]
+            out = t.copy() if out is None else np.maximum(out, t)
+    _arr(mask_out, (n, oh, ow), (oh * ow, ow, 1))[...] = out
+
+
+def pmfb_pixel_scale(inp, n, h, w, c, pre, act, alpha, beta, r, post, out, o_sn, o_sy, o_sx, rnd, stream):
+    v = _view(_deref(inp), n, h, w, c).astype(np.float32)
+    if pre:
+        v = v * _arr(pre, (n, h, w, 1), (h * w, w, 1, 1))
+    v = _act(act, v)
+    if alpha:
+        v = v * _vec(alpha, c)
+    if beta:
+        v = v + _vec(beta, c)
+    rv = _view(_deref(r), n, h, w, c) if r is not None else None
+    if rv is not None:
+        v = v + rv
+    if post:
+        v = v * _arr(post, (n, h, w, 1), (h * w, w, 1, 1))
+    if rnd:
+        v = rtf32(v)
+    _arr(out, (n, h, w, c), (o_sn, o_sy, o_sx, 1))[...] = v.astype(np.float32)
+
+
 _IMPL = {k: v for k, v in globals().items() if k.startswith("pmfb_")}
 
 

@@ -135,6 +135,22 @@ def gen_pmf(ref):
              grad_norms=gnorm, grad_names=gnames, **picks, **stats)
 
 
+def gen_epmf(ref):
+    from oracle import epmf_oracle as eo
+    for case in synth.EPMF_CASES:
+        torch.manual_seed(1)
+        m = ref.models.EPMFNet(pcd_channels=5, img_channels=3, nclasses=case["nclasses"], base_channels=32,
+                               imagenet_pretrained=False, image_backbone=case["backbone"])
+        shapes = eo.epmf_param_shapes(case["nclasses"], 32, case["backbone"])
+        assert list(shapes.keys()) == list(m.state_dict().keys())
+        m.load_state_dict(po.synth_state_dict(shapes, seed=case["seed"]), strict=True)
+        pcd, img = synth.epmf_inputs(case)
+        m.eval()
+        with torch.no_grad():
+            lid, cam = m(pcd, img)
+        save("epmf_%s.npz" % case["name"], lidar_eval=lid.numpy(), camera_eval=cam.numpy())
+
+
 def main():
     ref = load_reference()
     import importlib
@@ -145,6 +161,7 @@ def main():
     gen_project()
     gen_fusion(ref)
     gen_pmf(ref)
+    gen_epmf(ref)
 
 
 if __name__ == "__main__":

@@ -146,6 +146,16 @@ def fusion_inputs(case):
 PMF_CASES = [
     dict(name="r34_small", backbone="resnet34", nclasses=20, B=2, H=32, W=64, seed=1),
 ]
+EPMF_CASES = [
+    dict(name="r34_small", backbone="resnet34", nclasses=20, B=2, H=32, W=64, seed=4, density=0.15),
+]
+
+
+def epmf_inputs(case):
+    feat, _, _ = frame_tensor(case["B"], case["H"], case["W"], seed=case["seed"] + 200, density=case["density"])
+    return feat[:, 0:5].contiguous(), feat[:, 5:8].contiguous()
+
+
 PMF_GRAD_PICKS = [
     "lidar_stream.downCntx.conv1.weight", "lidar_stream.downCntx.conv2.weight", "camera_stream_encoder.conv1.weight",
     "lidar_stream.fusionblock_1.fuse_conv.2.weight", "lidar_stream.resBlock1.conv4.weight",

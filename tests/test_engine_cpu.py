@@ -202,3 +202,38 @@ def test_modules_refuse_cpu_tensors():
     m = M.ResidualBasedFusionBlock(8, 8)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 8, 4, 4), torch.zeros(1, 8, 4, 4))
+
+
+# ------------------------------------------------------------------------------------------------ EPMF (inference)
+def _epmf_case(B, H, W, seed, density=0.35):
+    from oracle import epmf_oracle as eo
+    torch.manual_seed(seed)
+    m = M.EPMFNet(5, 3, 20, 32, False, "resnet34")
+    sd = po.synth_state_dict(eo.epmf_param_shapes(20, 32, "resnet34"), seed=seed)
+    _load(m, sd)
+    feat, _, _ = synth.frame_tensor(B, H, W, seed=seed + 100, density=density)
+    return m, sd, feat[:, 0:5].contiguous(), feat[:, 5:8].contiguous()
+
+
+@pytest.mark.parametrize("density", [0.35, 0.03])
+def test_epmf_eval_matches_oracle(mock_exact, density):
+    """EPMFNet eval forward (sparse context blocks with their mask dilation incl. the stride-2 one, fusion-before-
+    ResBlock wiring at half resolution, extraUpSample, ASPP-fused camera decoder) against the oracle, exact arithmetic.
+    density 0.03: most 3x3 windows are empty, so the dilated masks actually zero large regions."""
+    from oracle import epmf_oracle as eo
+    from pmf_b200 import net as G
+    from pmf_b200.engine import Engine, WeightCache
+    m, sd, pcd, img = _epmf_case(1, 32, 64, 11, density)
+    m.eval()
+    with torch.no_grad():
+        E = Engine(G.ModuleParams(m), pcd.device, False, False, WeightCache(), dropout=False)
+        lid, cam, _, _ = G.epmf_forward(E, pcd, img, "resnet34", 20)
+        rl, rc = eo.epmf_forward(sd, pcd, img, "resnet34")
+    assert lid.shape == (1, 20, 32, 64) and cam.shape == (1, 20, 32, 64)
+    assert _maxrel(lid, rl) < 2e-5 and _maxrel(cam, rc) < 2e-5, (_maxrel(lid, rl), _maxrel(cam, rc))
+
+
+def test_epmf_rejects_training_and_bad_sizes():
+    m = M.EPMFNet(5, 3, 20, 32, False, "resnet34")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 5, 32, 32), torch.zeros(1, 3, 32, 32))

@@ -435,6 +435,65 @@ def test_pmf_resnet50_nuscenes_shaped(dev):
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
 
 
+# ------------------------------------------------------------------------------------------------ EPMF (inference)
+@pytest.mark.parametrize("case", synth.EPMF_CASES, ids=lambda c: c["name"])
+def test_epmf_eval_golden_and_oracle(dev, case):
+    """EPMFNet eval forward (BASELINE config 5's model; sparse context blocks, half-resolution LiDAR stream) against the
+    committed reference outputs and the tf32-operand oracle; CUDA-graph replay equals the eager result."""
+    import pmf_b200
+    from oracle import epmf_oracle as eo
+    torch.manual_seed(1)
+    m = pmf_b200.EPMFNet(5, 3, case["nclasses"], 32, False, case["backbone"])
+    sd = po.synth_state_dict(eo.epmf_param_shapes(case["nclasses"], 32, case["backbone"]), seed=case["seed"])
+    m.load_state_dict(sd, strict=True)
+    m.to(dev).eval()
+    pcd, img = synth.epmf_inputs(case)
+    gold = np.load(os.path.join(GOLDEN, "epmf_%s.npz" % case["name"]))
+    with torch.no_grad():
+        lid, cam = m(pcd.to(dev), img.to(dev))      # eager
+        lid2, cam2 = m(pcd.to(dev), img.to(dev))    # captured + replayed
+        rl, rc = eo.epmf_forward(sd, pcd, img, case["backbone"], tf32=True)
+    assert torch.equal(lid, lid2) and torch.equal(cam, cam2)
+    rep = dict(lidar_vs_reference=_maxrel(lid.cpu(), torch.from_numpy(gold["lidar_eval"])),
+               camera_vs_reference=_maxrel(cam.cpu(), torch.from_numpy(gold["camera_eval"])),
+               lidar_vs_tf32_oracle=_maxrel(lid.cpu(), rl), camera_vs_tf32_oracle=_maxrel(cam.cpu(), rc))
+    _report("epmf/golden_" + case["name"], rep)
+    assert rep["lidar_vs_reference"] < 5e-3 and rep["camera_vs_reference"] < 5e-3, rep
+    assert rep["lidar_vs_tf32_oracle"] < 5e-3 and rep["camera_vs_tf32_oracle"] < 5e-3, rep
+
+
+def test_epmf_eval_default_init_and_full_size(dev):
+    """Default initialisation: within 1e-3 of the fp32 reference arithmetic at 64x96; finite, normalised output at a
+    320x1280 frame (the EPMF KITTI shape, tasks/epmf/config_server_kitti.yaml:49-54); training mode is refused."""
+    import pmf_b200
+    from oracle import epmf_oracle as eo
+    torch.manual_seed(1)
+    m = pmf_b200.EPMFNet(5, 3, 20, 32, False, "resnet34")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m.to(dev).eval()
+    feat, _, _ = synth.frame_tensor(1, 64, 96, seed=23, density=0.2)
+    x = feat.to(dev)
+    with torch.no_grad():
+        lid, cam = m(x[:, 0:5], x[:, 5:8])
+        rl, rc = eo.epmf_forward(sd, feat[:, 0:5], feat[:, 5:8], "resnet34")
+    e = (_maxrel(lid.cpu(), rl), _maxrel(cam.cpu(), rc))
+    _report("epmf/eval_default_init", dict(lidar=e[0], camera=e[1]))
+    assert e[0] < 1e-3 and e[1] < 1e-3, e
+    feat, _, _ = synth.frame_tensor(1, 320, 1280, seed=24, density=0.1)
+    x = feat.to(dev)
+    with torch.no_grad():
+        lid, cam = m(x[:, 0:5], x[:, 5:8])
+    assert lid.shape == (1, 20, 320, 1280) and bool(torch.isfinite(lid).all()) and bool(torch.isfinite(cam).all())
+    assert float((lid.sum(1) - 1).abs().max()) < 1e-5 and float((cam.sum(1) - 1).abs().max()) < 1e-5
+    m.train()
+    with pytest.raises(NotImplementedError, match="inference-only"):
+        m(x[:, 0:5], x[:, 5:8])
+    m.eval()
+    with pytest.raises(AssertionError, match="invalid input size"):
+        with torch.no_grad():
+            m(torch.zeros(1, 5, 48, 64, device=dev), torch.zeros(1, 3, 48, 64, device=dev))
+
+
 def test_pmf_rejects_bad_sizes_and_cpu(dev):
     m, _ = _model(dev)
     with pytest.raises(AssertionError, match="invalid input size"):

@@ -102,6 +102,43 @@ def test_pmf_oracle_matches_golden(case):
         assert torch.allclose(ctx.new_stats[k], torch.from_numpy(ref["stat__" + k]), atol=1e-5, rtol=1e-5), k
 
 
+@pytest.mark.parametrize("case", synth.EPMF_CASES, ids=lambda c: c["name"])
+def test_epmf_oracle_matches_golden(case):
+    from oracle import epmf_oracle as eo
+    sd = po.synth_state_dict(eo.epmf_param_shapes(case["nclasses"], 32, case["backbone"]), seed=case["seed"])
+    pcd, img = synth.epmf_inputs(case)
+    ref = load("epmf_%s.npz" % case["name"])
+    with torch.no_grad():
+        lid, cam = eo.epmf_forward(sd, pcd, img, case["backbone"])
+    assert (lid - torch.from_numpy(ref["lidar_eval"])).abs().max() < 1e-6
+    assert (cam - torch.from_numpy(ref["camera_eval"])).abs().max() < 1e-6
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
+def test_epmf_oracle_equals_live_reference():
+    """EPMFNet: same state_dict inventory (689 keys, reference order), same default init under the same seed for our
+    module tree, and a bit-identical eval forward of the oracle on the reference's own initialisation."""
+    from oracle import epmf_oracle as eo
+    from oracle.ref_loader import load_reference
+    from pmf_b200 import modules as M
+    ref = load_reference()
+    torch.manual_seed(1)
+    m = ref.models.EPMFNet(5, 3, 20, 32, False, "resnet34")
+    shapes = eo.epmf_param_shapes(20, 32, "resnet34")
+    sd = m.state_dict()
+    assert list(shapes.keys()) == list(sd.keys())
+    assert all(tuple(v.shape) == tuple(shapes[k]) for k, v in sd.items())
+    torch.manual_seed(1)
+    ours = M.EPMFNet(5, 3, 20, 32, False, "resnet34").state_dict()
+    assert list(ours.keys()) == list(sd.keys()) and all(torch.equal(ours[k], sd[k]) for k in sd)
+    feat, _, _ = synth.frame_tensor(1, 32, 64, seed=6, density=0.2)
+    m.eval()
+    with torch.no_grad():
+        a, b = m(feat[:, :5], feat[:, 5:8])
+        a2, b2 = eo.epmf_forward(sd, feat[:, :5], feat[:, 5:8])
+    assert torch.equal(a, a2) and torch.equal(b, b2)
+
+
 @pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
 def test_oracle_equals_live_reference():
     from oracle.ref_loader import load_reference
