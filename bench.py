@@ -373,11 +373,47 @@ def inference_extras(model, d_feat, dev, B, H, W):
     ms_fwd, (lid, _cam) = ev_time(fwd, 5)
     ms_tail, _ = ev_time(lambda: tail(lid), 5)
     model.train(was_training)
-    return {"workload": "PMF-ResNet34 eval forward (batch %d, %dx%d) + argmax + KNN(k=5,S=5) of 32768 points/frame" % (B, H, W),
+    epmf = epmf_sweep(dev, H, W, knn, (pr, ur, px, py), ev_time)
+    return {"epmf_config5": epmf, "workload": "PMF-ResNet34 eval forward (batch %d, %dx%d) + argmax + KNN(k=5,S=5) of 32768 points/frame" % (B, H, W),
             "infer_fwd_frames_per_s": B / (ms_fwd * 1e-3), "infer_fwd_ms": ms_fwd,
             "knn_tail_ms_per_frame": ms_tail / B, "knn_points_per_s": B * 32768 / (ms_tail * 1e-3),
             "infer_plus_knn_frames_per_s": B / ((ms_fwd + ms_tail) * 1e-3),
             "fwd_tflops": FWD_KFLOP_PER_PX * 1e3 * H * W * B / (ms_fwd * 1e-3) / 1e12}
+
+
+def epmf_sweep(dev, H, W, knn, knn_in, ev_time, batches=(1, 8, 32)):
+    """BASELINE config 5: EPMF-ResNet34 inference-only (CUDA-graph replay) + argmax + KNN back-projection, batch sweep.
+    1097.2 kFLOP/pixel algorithmic forward."""
+    import pmf_b200
+    from tests import synth
+    torch.manual_seed(1)
+    m = pmf_b200.EPMFNet(5, 3, 20, 32, False, "resnet34").to(dev).eval()
+    pr, ur, px, py = knn_in
+    out = []
+    for B in batches:
+        feat, _, _ = synth.frame_tensor(B, H, W, seed=7, density=0.1)
+        x = feat.to(dev)
+
+        def fwd():
+            with torch.no_grad():
+                return m(x[:, 0:5], x[:, 5:8])
+
+        def tail(lid):
+            am = lid.argmax(1)
+            return [knn(pr, ur, am[b], px, py) for b in range(B)]
+
+        for _ in range(3):
+            lid, _cam = fwd()
+        tail(lid)
+        ms_fwd, (lid, _cam) = ev_time(fwd, 5)
+        ms_tail, _ = ev_time(lambda: tail(lid), 3)
+        out.append({"batch": B, "fwd_ms": ms_fwd, "fwd_frames_per_s": B / (ms_fwd * 1e-3),
+                    "fwd_plus_knn_frames_per_s": B / ((ms_fwd + ms_tail) * 1e-3),
+                    "fwd_tflops": 1097.2e3 * H * W * B / (ms_fwd * 1e-3) / 1e12})
+        del x
+        m._graphs.clear()
+        torch.cuda.empty_cache()
+    return {"workload": "EPMF-ResNet34 eval forward %dx%d + argmax + KNN(k=5,S=5) of 32768 points/frame" % (H, W), "sweep": out}
 
 
 def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
