@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PMFB_ABI_VERSION 1
+#define PMFB_ABI_VERSION 2
 #define PMFB_MAX_TAPS 9
 
 typedef enum {
@@ -89,6 +89,11 @@ typedef struct {
   float* out;
   int64_t o_sn, o_sy, o_sx; /* element strides of the output view (channel stride 1) */
   pmfb_epilogue epi;
+  /* Optional fused BatchNorm statistics of the epilogue result (nn.BatchNorm2d training mode, which follows every
+   * conv of salsanext.py / pmf_net.py / torchvision's blocks): bn_stats[0:c_out] += sum over all output pixels,
+   * bn_stats[c_out:2*c_out] += sum of squares (double accumulators, caller zeroes; same contract as pmfb_bn_stats).
+   * Only where pmfb_conv_fused_stats_ok(desc) returns 1; NULL = off. */
+  double* bn_stats;
 } pmfb_conv_desc;
 
 /* Weight gradient on tcgen05: dw[tap][ci][co] += sum_{n,y,x} x[n,y+dh,x+dw,..,dc+ci] * dy[n,y,x,co]
@@ -112,6 +117,9 @@ const char* pmfb_last_error(void);
 int pmfb_init(void);
 
 int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream);
+/* 1 if pmfb_conv_fwd can accumulate desc->bn_stats inside its epilogue for this geometry / epilogue (stride-1 layers on
+ * the halo kernel with a compile-time epilogue variant), else 0 (the caller then runs pmfb_bn_stats on the output). */
+int pmfb_conv_fused_stats_ok(const pmfb_conv_desc* d);
 int pmfb_conv_wgrad(const pmfb_wgrad_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmf_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_TAPS = 9
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
@@ -36,7 +36,7 @@ class ConvDesc(C.Structure):
                 ("tap_dh", i32 * MAX_TAPS), ("tap_wi", i32 * MAX_TAPS), ("use_tap_wi", i32), ("n_batch", i32),
                 ("out_h", i32), ("out_w", i32), ("tile_w", i32),
                 ("tile_h", i32), ("n_tile", i32), ("out", C.c_void_p), ("o_sn", i64), ("o_sy", i64), ("o_sx", i64),
-                ("epi", Epilogue)]
+                ("epi", Epilogue), ("bn_stats", C.c_void_p)]
 
 
 class WgradDesc(C.Structure):
@@ -59,6 +59,7 @@ _SIGNATURES = {
     "pmfb_last_error": ([], C.c_char_p),
     "pmfb_init": ([], C.c_int),
     "pmfb_conv_fwd": ([C.POINTER(ConvDesc), vp], C.c_int),
+    "pmfb_conv_fused_stats_ok": ([C.POINTER(ConvDesc)], C.c_int),
     "pmfb_conv_wgrad": ([C.POINTER(WgradDesc), vp], C.c_int),
     "pmfb_memset_zero": ([vp, C.c_size_t, vp], C.c_int),
     "pmfb_pack_input": ([vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, vp, i32, i64, i32, vp], C.c_int),
@@ -133,6 +134,11 @@ def call(name, *args):
     global launches
     launches += 1
     check(getattr(lib(), name)(*args), name)
+
+
+def query(name, *args):
+    """Entry points that answer a question (return value is the answer, not a status)."""
+    return int(getattr(lib(), name)(*args))
 
 
 _inited = False

@@ -44,6 +44,7 @@ struct HaloK {
   float* out;
   long long o_sn, o_sy, o_sx;
   EpiParams epi;
+  double* bn_stats;
 };
 
 __device__ __forceinline__ uint64_t desc_with_base(uint32_t saddr, uint32_t lbo, uint32_t sbo, int use_base_off) {
@@ -59,6 +60,13 @@ __device__ __forceinline__ uint64_t desc_with_base(uint32_t saddr, uint32_t lbo,
 // dependency bound at 1.4 TB/s of stores) and every thin full-resolution layer pinned to that rate.
 constexpr int kEpiGeneric = -1;
 constexpr int kEpiB1 = 1, kEpiR1 = 2, kEpiRnd = 4, kEpiLeaky = 8;
+// kEpiStats: BatchNorm batch statistics of the epilogue result, fused.  After a warp has parked its 32-pixel x 32-channel
+// unit in the staging tile, lane c re-reads COLUMN c (32 conflict-free 4-byte loads: the 128B swizzle permutes the
+// 16-byte chunks of a row, so the 32 lanes of one row read hit 32 different banks), adds the 32 values and their squares
+// and issues two shared-memory float atomics into per-CTA channel sums; the CTA flushes them once, at its end, with
+// fp64 atomics (pmfb_bn_stats contract).  Saves the separate statistics pass over every pre-BN activation.
+constexpr int kEpiStats = 16;
+constexpr int kHStatsC = 256;  // fused statistics: c_out <= 256 (2 x 256 fp64 accumulators in the unused alpha2/beta2 slots)
 
 template <int EPI>
 __global__ void __launch_bounds__(kHThreads, 1)
@@ -105,6 +113,10 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
     for (int k = 0; k < 4; ++k)
       if (src[k])
         for (int c = threadIdx.x; c < P.c_out; c += kHThreads) sv[k * kHMaxC + c] = __ldg(src[k] + c);
+  }
+  if constexpr (EPI != kEpiGeneric && (EPI & kEpiStats) != 0) {  // per-CTA channel sums live in the unused alpha2/beta2 slots
+    double* ds = reinterpret_cast<double*>(smem + 1024 + 2 * kHMaxC * 4);  // [0:256) sums, [256:512) sums of squares
+    for (int c = threadIdx.x; c < 2 * kHStatsC; c += kHThreads) ds[c] = 0.0;
   }
   tc_fence_before();
   __syncthreads();
@@ -275,6 +287,27 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
               bulk_commit_group();
             }
           }
+          if constexpr ((EPI & kEpiStats) != 0) {
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+            if (lane < 4 * nq) {
+              const uint32_t col = smem_u32(stage) + (uint32_t)((lane & 3) << 2);
+              const uint32_t chunk = (uint32_t)(lane >> 2);
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                if ((vmask >> r) & 1u) {
+                  const float t = ld_shared_f32(col + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4));
+                  s1 += t;
+                  s2 += t * t;
+                }
+              }
+              // fp64 shared accumulators: the order of the atomics must not show (a replayed step has to reproduce
+              // an eager one, and near-constant channels turn fp32 ordering noise into percent-level BN changes)
+              double* acc = reinterpret_cast<double*>(smem + 1024 + 2 * kHMaxC * 4) + c0 + lane;
+              atomicAdd(acc, (double)s1);
+              atomicAdd(acc + kHStatsC, (double)s2);
+            }
+          }
         }
       } else
       for (int u = half; u < units; u += 2) {
@@ -345,6 +378,13 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  if constexpr (EPI != kEpiGeneric && (EPI & kEpiStats) != 0) {
+    const double* ds = reinterpret_cast<const double*>(smem + 1024 + 2 * kHMaxC * 4);
+    for (int c = threadIdx.x; c < P.c_out; c += kHThreads) {
+      atomicAdd(P.bn_stats + c, ds[c]);
+      atomicAdd(P.bn_stats + P.c_out + c, ds[kHStatsC + c]);
+    }
+  }
 }
 
 static int pow2_cols_h(int n) {
@@ -386,9 +426,33 @@ static int launch_halo_variant(int epi, int grid, size_t smem, cudaStream_t stre
 #define PMFB_HV(e) case e: return launch_halo_t<e>(grid, smem, stream, tmx, tmw, tmo, P);
     PMFB_HV(0) PMFB_HV(1) PMFB_HV(2) PMFB_HV(3) PMFB_HV(4) PMFB_HV(5) PMFB_HV(6) PMFB_HV(7)
     PMFB_HV(8) PMFB_HV(9) PMFB_HV(12) PMFB_HV(13)
+    PMFB_HV(16) PMFB_HV(17) PMFB_HV(24) PMFB_HV(25)
 #undef PMFB_HV
     default: return launch_halo_t<kEpiGeneric>(grid, smem, stream, tmx, tmw, tmo, P);
   }
+}
+
+static int halo_fast_epi(const pmfb_conv_desc* d) {
+  const pmfb_epilogue& E = d->epi;
+  if (!E.alpha1 && !E.alpha2 && !E.beta2 && !E.mul.ptr && !E.r2.ptr && (E.act == PMFB_ACT_NONE || E.act == PMFB_ACT_LEAKY) &&
+      !(E.r1.ptr && E.act != PMFB_ACT_NONE))
+    return (E.beta1 ? kEpiB1 : 0) | (E.r1.ptr ? kEpiR1 : 0) | (E.round_out ? kEpiRnd : 0) | (E.act == PMFB_ACT_LEAKY ? kEpiLeaky : 0);
+  return kEpiGeneric;
+}
+
+// Fused BN statistics: stride-1 halo layers whose epilogue is [+bias] [LeakyReLU] without rounding / accumulation, with the
+// bulk-store epilogue (its staging tile is what the statistics read) and blocks that are multiples of 32 channels.
+int halo_fused_stats_ok(const pmfb_conv_desc* d) {
+  const char* e = getenv("PMFB_HALO_TMA_STORE");
+  if (e && !atoi(e)) return 0;
+  const char* f = getenv("PMFB_HALO_FAST_EPI");
+  if (f && !atoi(f)) return 0;
+  const char* g = getenv("PMFB_FUSED_BN_STATS");
+  if (g && !atoi(g)) return 0;
+  const int epi = halo_fast_epi(d);
+  if (epi == kEpiGeneric || (epi & (kEpiR1 | kEpiRnd))) return 0;
+  if ((reinterpret_cast<uintptr_t>(d->out) & 15) || d->o_sx % 4 || d->o_sy % 4 || d->o_sn % 4) return 0;
+  return d->c_out <= kHStatsC ? 1 : 0;
 }
 
 int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
@@ -531,10 +595,12 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
     const char* e = getenv("PMFB_HALO_FAST_EPI");
     fast_mode = e ? atoi(e) : 1;
   }
-  const pmfb_epilogue& E = d->epi;
-  if (fast_mode && !E.alpha1 && !E.alpha2 && !E.beta2 && !E.mul.ptr && !E.r2.ptr &&
-      (E.act == PMFB_ACT_NONE || E.act == PMFB_ACT_LEAKY) && !(E.r1.ptr && E.act != PMFB_ACT_NONE)) {
-    epi = (E.beta1 ? kEpiB1 : 0) | (E.r1.ptr ? kEpiR1 : 0) | (E.round_out ? kEpiRnd : 0) | (E.act == PMFB_ACT_LEAKY ? kEpiLeaky : 0);
+  if (fast_mode) epi = halo_fast_epi(d);
+  P.bn_stats = d->bn_stats;
+  if (d->bn_stats) {
+    if (!halo_fused_stats_ok(d) || !P.tma_store || epi == kEpiGeneric)
+      return fail(PMFB_ERR_INVALID, "conv halo: fused BN statistics are not available for this layer");
+    epi |= kEpiStats;
   }
   return launch_halo_variant(epi, grid, smem, (cudaStream_t)stream, tmx, tmw, tmo, P);
 }

@@ -314,11 +314,19 @@ static const int kSmemBudget = 200 * 1024;
 namespace pmfb {
 int halo_eligible(const pmfb_conv_desc* d);
 int launch_conv_halo(const pmfb_conv_desc* d, void* stream);
+int halo_fused_stats_ok(const pmfb_conv_desc* d);
 int wgrad_halo_eligible(const pmfb_wgrad_desc* d);
 int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream);
 }  // namespace pmfb
 
 using namespace pmfb;
+
+extern "C" int pmfb_conv_fused_stats_ok(const pmfb_conv_desc* d) {
+  if (!d || d->n_taps < 1 || d->n_taps > PMFB_MAX_TAPS) return 0;
+  const char* e = getenv("PMFB_CONV_V1");
+  if (e && atoi(e)) return 0;
+  return (halo_eligible(d) && halo_fused_stats_ok(d)) ? 1 : 0;
+}
 
 extern "C" int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream) {
   if (!d) return fail(PMFB_ERR_INVALID, "null desc");
@@ -336,6 +344,7 @@ extern "C" int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream) {
     }
     if (!force_v1 && halo_eligible(d)) return launch_conv_halo(d, stream);
   }
+  if (d->bn_stats) return fail(PMFB_ERR_INVALID, "conv_fwd: fused BN statistics are not available for this layer (query pmfb_conv_fused_stats_ok)");
   if (d->tile_w * d->tile_h != kTileM) return fail(PMFB_ERR_INVALID, "tile_w*tile_h must be 128");
   if (d->n_tile < 16 || d->n_tile > 256 || d->n_tile % 16)
     return fail(PMFB_ERR_INVALID, "n_tile=%d must be a multiple of 16 in [16,256]", d->n_tile);

@@ -423,7 +423,8 @@ class Engine:
             s.strides[:] = [2 * sx * 4, sy * 4, 2 * sy * 4, sn * 4]
         return s
 
-    def _conv_launch(self, x_t, c_in, stride2, w_packed, c_out, taps, n, out_h, out_w, out_t, epi):
+    def _conv_launch(self, x_t, c_in, stride2, w_packed, c_out, taps, n, out_h, out_w, out_t, epi, bn_stats=None):
+        """Returns True when ``bn_stats`` (2*c_out fp64 sums, zeroed) was accumulated by the conv's own epilogue."""
         d = ConvDesc()
         d.x = self._tma_src(x_t, c_in, stride2)
         d.w = w_packed.data_ptr()
@@ -437,9 +438,15 @@ class Engine:
         d.out = out_t.data_ptr()
         d.o_sn, d.o_sy, d.o_sx = out_t.stride(0), out_t.stride(1), out_t.stride(2)
         d.epi = epi
+        d.bn_stats = None
+        fused = False
+        if bn_stats is not None and L.query("pmfb_conv_fused_stats_ok", C.byref(d)) == 1:
+            d.bn_stats = bn_stats.data_ptr()
+            fused = True
         L.call("pmfb_conv_fwd", C.byref(d), self.st)
+        return fused
 
-    def _conv_fwd(self, x, cp, out_t, epi):
+    def _conv_fwd(self, x, cp, out_t, epi, bn_stats=None):
         """out = epi(conv(x)); x: Act whose channel count equals cp.c_in_p."""
         e = self.cache.get(cp, self.record, self.st)
         n, h, w, cx = x.shape
@@ -450,10 +457,11 @@ class Engine:
             oh = (h + 2 * cp.pad - cp.dil * (cp.kh - 1) - 1) // cp.stride + 1
             ow = (w + 2 * cp.pad - cp.dil * (cp.kw - 1) - 1) // cp.stride + 1
         assert tuple(out_t.shape) == (n, oh, ow, cp.c_out_p), (cp.name, tuple(out_t.shape), (n, oh, ow, cp.c_out_p))
-        self._conv_launch(x.t, cp.c_in_p, cp.stride == 2, e["fwd"], cp.c_out_p, cp.fwd_taps(), n, oh, ow, out_t, epi)
+        fused = self._conv_launch(x.t, cp.c_in_p, cp.stride == 2, e["fwd"], cp.c_out_p, cp.fwd_taps(), n, oh, ow, out_t, epi,
+                                  bn_stats=bn_stats)
         if self.record:
             self._wg_list.append(cp)
-        return e
+        return fused if bn_stats is not None else e
 
     def prepare_backward(self):
         """Graph mode, called once BEFORE the backward capture: one arena for every packed weight gradient (zeroed by a
@@ -550,11 +558,21 @@ class Engine:
                bn.running_var.data_ptr(), bn.momentum, bn.eps, alpha.data_ptr(), beta.data_ptr(), None, None, self.st)
         return alpha, beta
 
-    def _bn_train_affine(self, bn, a_t):
+    def _conv_fwd_with_stats(self, x, cp, bn, out_t, epi):
+        """conv into out_t + the training-mode BatchNorm statistics of the result: fused into the conv's epilogue where
+        the library supports it (pmfb_conv_fused_stats_ok), else by a separate pmfb_bn_stats pass."""
+        assert cp.c_out_p == bn.c
+        sums = self.d64.take(2 * bn.c)
+        fused = self._conv_fwd(x, cp, out_t, epi, bn_stats=sums)
+        return self._bn_train_affine(bn, out_t, sums=sums, have_sums=fused)
+
+    def _bn_train_affine(self, bn, a_t, sums=None, have_sums=False):
         n, h, w, c = a_t.shape
         assert c == bn.c
-        sums = self.d64.take(2 * c)
-        L.call("pmfb_bn_stats", C.byref(_view(a_t)), n, h, w, c, sums.data_ptr(), self.st)
+        if sums is None:
+            sums = self.d64.take(2 * c)
+        if not have_sums:
+            L.call("pmfb_bn_stats", C.byref(_view(a_t)), n, h, w, c, sums.data_ptr(), self.st)
         v = self.f32.take(4 * c)
         alpha, beta, mean, invstd = v[:c], v[c:2 * c], v[2 * c:3 * c], v[3 * c:]
         L.call("pmfb_bn_finalize", sums.data_ptr(), n * h * w, c, _p(bn.weight.detach()), _p(bn.bias.detach()),
@@ -639,8 +657,7 @@ class Engine:
             self._conv_fwd(x, cp, y.t, self._epi(beta1=e["bias"], act=ACT_LEAKY, alpha2=alpha, beta2=beta, r2=sc_t, rnd=1))
             return y
         a = torch.empty(shp, device=self.device, dtype=torch.float32)
-        self._conv_fwd(x, cp, a, self._epi(beta1=e["bias"], act=ACT_LEAKY))
-        stats = self._bn_train_affine(bn, a)
+        stats = self._conv_fwd_with_stats(x, cp, bn, a, self._epi(beta1=e["bias"], act=ACT_LEAKY))
         mv = None if mask is None else _chan_view(mask)
         self.pointwise(a, y.t, alpha1=stats[0], beta1=stats[1], r1=sc_t, mul=mv, rnd=1)
         if self.record:
@@ -676,8 +693,7 @@ class Engine:
                                                  rnd=1 if rnd else 0))
             return y
         c_t = torch.empty(shp, device=self.device, dtype=torch.float32)
-        self._conv_fwd(x, cp, c_t, self._epi(beta1=e["bias"]))
-        stats = self._bn_train_affine(bn, c_t)
+        stats = self._conv_fwd_with_stats(x, cp, bn, c_t, self._epi(beta1=e["bias"]))
         mv = None if mask is None else _chan_view(mask)
         self.pointwise(c_t, y.t, alpha1=stats[0], beta1=stats[1], r1=id_t, act=post, mul=f_t if gate is not None else mv,
                        r2=pcd_t, rnd=1 if rnd else 0)

@@ -406,6 +406,24 @@ def pmfb_conv_fwd(dp_, stream):
         acc += (a.reshape(-1, d.c_in) @ Wp[wi].T).reshape(acc.shape)
     res = _epilogue(d.epi, acc, d.n_batch, d.out_h, d.out_w, d.c_out)
     _arr(d.out, acc.shape, (d.o_sn, d.o_sy, d.o_sx, 1))[...] = res
+    if d.bn_stats:  # fused BatchNorm statistics of the epilogue result (pmfb_bn_stats contract)
+        st = _vec(d.bn_stats, 2 * d.c_out, np.float64)
+        v = res.astype(np.float64)
+        st[:d.c_out] += v.sum((0, 1, 2))
+        st[d.c_out:] += (v * v).sum((0, 1, 2))
+
+
+def pmfb_conv_fused_stats_ok(dp_):
+    """Model of the library's answer: stride-1 layers (parity dimension 1) with taps inside the +-2 / +-3 halo and a
+    [+bias][LeakyReLU] epilogue; everything else falls back to pmfb_bn_stats."""
+    d = _deref(dp_)
+    e = d.epi
+    if d.x.dims[2] != 1 or e.alpha1 or e.alpha2 or e.beta2 or e.mul.ptr or e.r2.ptr or e.r1.ptr or e.round_out:
+        return 0
+    if e.act not in (L.ACT_NONE, L.ACT_LEAKY):
+        return 0
+    return int(all(abs(d.tap_dw[i]) <= 2 and abs(d.tap_dh[i]) <= 3 and d.tap_dp[i] == 0 and d.tap_dc[i] == 0
+                   for i in range(d.n_taps)))
 
 
 def pmfb_conv_wgrad(dp_, stream):
@@ -476,5 +494,6 @@ def install(monkeypatch, exact=False):
         _IMPL[name](*args)
 
     monkeypatch.setattr(L, "call", call)
+    monkeypatch.setattr(L, "query", lambda name, *args: int(_IMPL[name](*args)))
     monkeypatch.setattr(L, "require_device", lambda: None)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _FakeStream())
