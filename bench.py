@@ -30,7 +30,7 @@ import torch  # noqa: E402
 FWD_KFLOP_PER_PX = 1806.6   # PMF-ResNet34 forward, 2*MAC, convs only
 STEP_KFLOP_PER_PX = 5400.7  # forward + dgrad + wgrad (minus the two input dgrads)
 METRIC = "frames/sec PMF-ResNet34 fwd+bwd (480x640 camera grid, batch 8/GPU)"
-NCU_HALO_DRAM_BYTES_PER_LAUNCH = (38.85e9 + 22.47e9) / 199  # see kernel_roofline()
+NCU_HALO_DRAM_BYTES_PER_LAUNCH = 63.54e9 / 205  # see kernel_roofline()
 
 
 def parse():
@@ -535,9 +535,9 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
     return {"bound": "tensor", "kernel": "conv_fwd_halo_kernel / conv_fwd_tc_kernel (tcgen05 kind::tf32 implicit GEMM: forward + dgrad launches)",
             "achieved": dom["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": dom["tflops"] / peak_tf,
             "peak_source": peak_src + "; kind::tf32 issues at half the bf16 rate, so 0.5 is this kernel's ceiling",
-            # DRAM bytes per launch of this kernel: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 199
-            # conv_fwd_halo_kernel launches of one step (profiles/r1_launches_step_b8_480x640_final.csv: 38.85 GB read +
-            # 22.47 GB written) / 199; the algorithmic figure of the same launches is `alg_bytes_per_launch`.
+            # DRAM bytes per launch of this kernel: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 205
+            # conv_fwd_halo_kernel launches of one step (profiles/r1_launch_summary_final.txt: 63.54 GB) / 205; the
+            # algorithmic figure of the same launches is `alg_bytes_per_launch`.
             "traffic": NCU_HALO_DRAM_BYTES_PER_LAUNCH, "alg_bytes_per_launch": by["pmfb_conv_fwd"][3] / max(dom["launches"], 1),
             "launches_per_step": dom["launches"], "ms_in_kernel_per_step": dom["ms"],
             "share_of_step": dom["ms"] / max(in_kernels, 1e-9),

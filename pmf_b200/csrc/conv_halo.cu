@@ -66,6 +66,10 @@ constexpr int kEpiB1 = 1, kEpiR1 = 2, kEpiRnd = 4, kEpiLeaky = 8;
 // and issues two shared-memory float atomics into per-CTA channel sums; the CTA flushes them once, at its end, with
 // fp64 atomics (pmfb_bn_stats contract).  Saves the separate statistics pass over every pre-BN activation.
 constexpr int kEpiStats = 16;
+// Eval-mode fusions (inference: BASELINE config 5): alpha1 scale (eval BN folded in front of the activation: torchvision
+// conv -> BN -> ReLU), ReLU, the post-activation affine alpha2/beta2 (SalsaNext conv -> LeakyReLU -> BN) and the second
+// residual r2 (ResContextBlock / ResBlock shortcut).  Only the combinations listed in launch_halo_variant exist.
+constexpr int kEpiA1 = 32, kEpiRelu = 64, kEpiA2B2 = 128, kEpiR2 = 256;
 constexpr int kHStatsC = 256;  // fused statistics: c_out <= 256 (2 x 256 fp64 accumulators in the unused alpha2/beta2 slots)
 
 template <int EPI>
@@ -254,6 +258,14 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                 if (i < nq) r1v[i] = ld4(r1p + 4 * i);
             }
           }
+          if constexpr ((EPI & kEpiR2) != 0) {  // never together with r1: the same registers hold it
+            const float* r2p = P.epi.r2.p + ((long long)n_img * P.epi.r2.sn + (long long)y * P.epi.r2.sy + (long long)x * P.epi.r2.sx) + c0;
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < nq) r1v[i] = ld4(r2p + 4 * i);
+            }
+          }
           tmem_ld_wait();
           if (tma_store) {  // the previous unit's store must have finished reading the staging tile
             if (lane == 0) bulk_wait_group_read0();
@@ -264,6 +276,10 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
             for (int i = 0; i < 8; ++i) {
               if (i < nq) {
                 float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                if constexpr ((EPI & kEpiA1) != 0) {
+                  const float4 a = *reinterpret_cast<const float4*>(sv + c0 + 4 * i);
+                  o.x *= a.x; o.y *= a.y; o.z *= a.z; o.w *= a.w;
+                }
                 if constexpr ((EPI & kEpiB1) != 0) {
                   const float4 b = *reinterpret_cast<const float4*>(sv + kHMaxC + c0 + 4 * i);
                   o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
@@ -273,6 +289,15 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                   o.x = fmaxf(o.x, 0.01f * o.x); o.y = fmaxf(o.y, 0.01f * o.y);
                   o.z = fmaxf(o.z, 0.01f * o.z); o.w = fmaxf(o.w, 0.01f * o.w);
                 }
+                if constexpr ((EPI & kEpiRelu) != 0) {  // v > 0 ? v : 0, as epi_act (NaN -> 0)
+                  o.x = o.x > 0.f ? o.x : 0.f; o.y = o.y > 0.f ? o.y : 0.f; o.z = o.z > 0.f ? o.z : 0.f; o.w = o.w > 0.f ? o.w : 0.f;
+                }
+                if constexpr ((EPI & kEpiA2B2) != 0) {
+                  const float4 a = *reinterpret_cast<const float4*>(sv + 2 * kHMaxC + c0 + 4 * i);
+                  const float4 b = *reinterpret_cast<const float4*>(sv + 3 * kHMaxC + c0 + 4 * i);
+                  o.x = o.x * a.x + b.x; o.y = o.y * a.y + b.y; o.z = o.z * a.z + b.z; o.w = o.w * a.w + b.w;
+                }
+                if constexpr ((EPI & kEpiR2) != 0) { o.x += r1v[i].x; o.y += r1v[i].y; o.z += r1v[i].z; o.w += r1v[i].w; }
                 if constexpr ((EPI & kEpiRnd) != 0) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
                 if (tma_store) st_shared_v4(st_row + ((((uint32_t)i) ^ st_x) << 4), o);
                 else *reinterpret_cast<float4*>(optr + 4 * i) = o;
@@ -427,6 +452,9 @@ static int launch_halo_variant(int epi, int grid, size_t smem, cudaStream_t stre
     PMFB_HV(0) PMFB_HV(1) PMFB_HV(2) PMFB_HV(3) PMFB_HV(4) PMFB_HV(5) PMFB_HV(6) PMFB_HV(7)
     PMFB_HV(8) PMFB_HV(9) PMFB_HV(12) PMFB_HV(13)
     PMFB_HV(16) PMFB_HV(17) PMFB_HV(24) PMFB_HV(25)
+    PMFB_HV(kEpiB1 | kEpiLeaky | kEpiA2B2 | kEpiRnd) PMFB_HV(kEpiB1 | kEpiLeaky | kEpiA2B2 | kEpiRnd | kEpiR2)
+    PMFB_HV(kEpiA1 | kEpiB1 | kEpiRelu | kEpiRnd) PMFB_HV(kEpiA1 | kEpiB1 | kEpiRelu | kEpiRnd | kEpiR1)
+    PMFB_HV(kEpiA1 | kEpiB1 | kEpiRnd)
 #undef PMFB_HV
     default: return launch_halo_t<kEpiGeneric>(grid, smem, stream, tmx, tmw, tmo, P);
   }
@@ -434,10 +462,25 @@ static int launch_halo_variant(int epi, int grid, size_t smem, cudaStream_t stre
 
 static int halo_fast_epi(const pmfb_conv_desc* d) {
   const pmfb_epilogue& E = d->epi;
-  if (!E.alpha1 && !E.alpha2 && !E.beta2 && !E.mul.ptr && !E.r2.ptr && (E.act == PMFB_ACT_NONE || E.act == PMFB_ACT_LEAKY) &&
-      !(E.r1.ptr && E.act != PMFB_ACT_NONE))
-    return (E.beta1 ? kEpiB1 : 0) | (E.r1.ptr ? kEpiR1 : 0) | (E.round_out ? kEpiRnd : 0) | (E.act == PMFB_ACT_LEAKY ? kEpiLeaky : 0);
-  return kEpiGeneric;
+  if (E.mul.ptr || E.act == PMFB_ACT_SIGMOID || (E.alpha2 != nullptr) != (E.beta2 != nullptr)) return kEpiGeneric;
+  int m = (E.alpha1 ? kEpiA1 : 0) | (E.beta1 ? kEpiB1 : 0) | (E.r1.ptr ? kEpiR1 : 0) | (E.round_out ? kEpiRnd : 0) |
+          (E.act == PMFB_ACT_LEAKY ? kEpiLeaky : 0) | (E.act == PMFB_ACT_RELU ? kEpiRelu : 0) | (E.alpha2 ? kEpiA2B2 : 0) |
+          (E.r2.ptr ? kEpiR2 : 0);
+  // note: alpha2/beta2 in the fast path are one fused multiply-add, the generic path multiplies then adds (same fp32
+  // results up to the fma's single rounding; within the 1e-3 parity bar, eval mode only)
+  switch (m) {
+    // training step: [+bias][LeakyReLU][round], [+= r1][round]
+    case 0: case 1: case 4: case 5: case 8: case 9: case 12: case 13: case 2: case 6:
+    // inference: conv -> LeakyReLU -> BN(eval) [+ shortcut]; conv -> BN(eval) [+ identity] -> ReLU; conv -> BN(eval)
+    case kEpiB1 | kEpiLeaky | kEpiA2B2 | kEpiRnd:
+    case kEpiB1 | kEpiLeaky | kEpiA2B2 | kEpiRnd | kEpiR2:
+    case kEpiA1 | kEpiB1 | kEpiRelu | kEpiRnd:
+    case kEpiA1 | kEpiB1 | kEpiRelu | kEpiRnd | kEpiR1:
+    case kEpiA1 | kEpiB1 | kEpiRnd:
+      return m;
+    default:
+      return kEpiGeneric;
+  }
 }
 
 // Fused BN statistics: stride-1 halo layers whose epilogue is [+bias] [LeakyReLU] without rounding / accumulation, with the
@@ -450,7 +493,7 @@ int halo_fused_stats_ok(const pmfb_conv_desc* d) {
   const char* g = getenv("PMFB_FUSED_BN_STATS");
   if (g && !atoi(g)) return 0;
   const int epi = halo_fast_epi(d);
-  if (epi == kEpiGeneric || (epi & (kEpiR1 | kEpiRnd))) return 0;
+  if (epi == kEpiGeneric || (epi & ~(kEpiB1 | kEpiLeaky))) return 0;
   if ((reinterpret_cast<uintptr_t>(d->out) & 15) || d->o_sx % 4 || d->o_sy % 4 || d->o_sn % 4) return 0;
   return d->c_out <= kHStatsC ? 1 : 0;
 }

@@ -780,33 +780,34 @@ mask_maxpool_kernel(const float* __restrict__ in, int n, int h, int w, int k, in
   }
 }
 
-// out = (act(in * pre[p]) * alpha[c] + beta[c] + r) * post[p], optional tf32 rounding; thread = (pixel, float4 group)
+// out = (act(in * pre[p]) * alpha[c] + beta[c] + r) * post[p], optional tf32 rounding; thread = (pixel, float4 group).
+// 32-bit indexing; pixel-linear views (offset = pixel * sx: dense tensors and channel slices of concat buffers) skip the
+// (n, y, x) decode.
+__device__ __forceinline__ long long px_off(const EpiView& v, int linear, unsigned pix, unsigned hw, unsigned w) {
+  if (linear) return (long long)pix * v.sx;
+  const unsigned n = pix / hw, q = pix - n * hw, y = q / w, x = q - y * w;
+  return (long long)n * v.sn + (long long)y * v.sy + (long long)x * v.sx;
+}
+
 __global__ void __launch_bounds__(256)
-pixel_scale_kernel(EpiView in, int n, int h, int w, int c4, const float* __restrict__ pre, int act, const float* __restrict__ alpha,
-                   const float* __restrict__ beta, EpiView r, const float* __restrict__ post, float* out, long long o_sn,
-                   long long o_sy, long long o_sx, int round_out) {
-  const long long total = (long long)n * h * w * c4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % c4);
-    long long p = i / c4;
-    const long long pix = p;
-    const int xx = (int)(p % w);
-    p /= w;
-    const int yy = (int)(p % h);
-    const int ni = (int)(p / h);
-    const int c = 4 * g;
-    float4 v = ld4(in.p + (long long)ni * in.sn + (long long)yy * in.sy + (long long)xx * in.sx + c);
-    if (pre) { const float m = pre[pix]; v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
+pixel_scale_kernel(EpiView in, int lin_in, unsigned npix, unsigned hw, unsigned w, unsigned c4, const float* __restrict__ pre, int act,
+                   const float* __restrict__ alpha, const float* __restrict__ beta, EpiView r, int lin_r,
+                   const float* __restrict__ post, EpiView out, int lin_out, int round_out) {
+  const unsigned total = npix * c4;  // host guarantees < 2^32
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned pix = i / c4;
+    const int c = 4 * (int)(i - pix * c4);
+    float4 v = ld4(in.p + px_off(in, lin_in, pix, hw, w) + c);
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r.p) q = ld4(r.p + px_off(r, lin_r, pix, hw, w) + c);
+    if (pre) { const float m = __ldg(pre + pix); v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
     if (act) { v.x = epi_act(act, v.x); v.y = epi_act(act, v.y); v.z = epi_act(act, v.z); v.w = epi_act(act, v.w); }
     if (alpha) { const float4 a = ld4(alpha + c); v.x *= a.x; v.y *= a.y; v.z *= a.z; v.w *= a.w; }
     if (beta) { const float4 b = ld4(beta + c); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
-    if (r.p) {
-      const float4 q = ld4(r.p + (long long)ni * r.sn + (long long)yy * r.sy + (long long)xx * r.sx + c);
-      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-    }
-    if (post) { const float m = post[pix]; v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
+    v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    if (post) { const float m = __ldg(post + pix); v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
     if (round_out) v = rnd4(v);
-    *reinterpret_cast<float4*>(out + (long long)ni * o_sn + (long long)yy * o_sy + (long long)xx * o_sx + c) = v;
+    *reinterpret_cast<float4*>(const_cast<float*>(out.p) + px_off(out, lin_out, pix, hw, w) + c) = v;
   }
 }
 
@@ -842,9 +843,17 @@ extern "C" int pmfb_pixel_scale(const pmfb_view* in, int32_t n, int32_t h, int32
   REQ(act >= 0 && act <= 3, "pixel_scale: act=%d", act);
   const long long total = (long long)n * h * w * (c / 4);
   if (total == 0) return PMFB_OK;
-  pixel_scale_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(in), n, h, w, c / 4, pre_mask, act, alpha, beta,
-                                                                             r ? ev(r) : ev(nullptr), post_mask, out, o_sn, o_sy,
-                                                                             o_sx, round_out);
+  REQ(total < (1ll << 32), "pixel_scale: tensor too large for 32-bit indexing");
+  auto lin = [&](long long sn, long long sy, long long sx) { return (sy == (long long)w * sx && sn == (long long)h * sy) ? 1 : 0; };
+  EpiView vo;
+  vo.p = out;
+  vo.sn = o_sn;
+  vo.sy = o_sy;
+  vo.sx = o_sx;
+  const EpiView vr = (r && r->ptr) ? ev(r) : ev(nullptr);
+  pixel_scale_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      ev(in), lin(in->sn, in->sy, in->sx), (unsigned)((long long)n * h * w), (unsigned)(h * w), (unsigned)w, (unsigned)(c / 4), pre_mask,
+      act, alpha, beta, vr, vr.p ? lin(vr.sn, vr.sy, vr.sx) : 0, post_mask, vo, lin(o_sn, o_sy, o_sx), round_out);
   PMFB_LAUNCH_CHECK("pixel_scale_kernel");
   return PMFB_OK;
 }
