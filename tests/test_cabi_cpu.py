@@ -56,8 +56,11 @@ def test_struct_layout_matches_c():
     src = r'''
     #include <stdio.h>
     #include "pmfb.h"
-    int main(){ printf("%zu %zu %zu %zu %zu\n", sizeof(pmfb_view), sizeof(pmfb_epilogue), sizeof(pmfb_tma_src),
-                       sizeof(pmfb_conv_desc), sizeof(pmfb_wgrad_desc)); return 0; }
+    #include <stddef.h>
+    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pmfb_view), sizeof(pmfb_epilogue), sizeof(pmfb_tma_src),
+                       sizeof(pmfb_conv_desc), sizeof(pmfb_wgrad_desc), sizeof(pmfb_weight_job),
+                       offsetof(pmfb_weight_job, c_out), offsetof(pmfb_weight_job, start), offsetof(pmfb_conv_desc, bn_stats));
+                return 0; }
     '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -65,4 +68,22 @@ def test_struct_layout_matches_c():
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")], check=True)
         sizes = [int(x) for x in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(_lib.View), C.sizeof(_lib.Epilogue), C.sizeof(_lib.TmaSrc), C.sizeof(_lib.ConvDesc),
-                     C.sizeof(_lib.WgradDesc)]
+                     C.sizeof(_lib.WgradDesc), C.sizeof(_lib.WeightJob), _lib.WeightJob.c_out.offset, _lib.WeightJob.start.offset,
+                     _lib.ConvDesc.bn_stats.offset]
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port) prints ONE JSON line with the contract's
+    keys; run on a tiny frame so that the CPU suite stays fast."""
+    import json
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--height", "32", "--width", "64"], capture_output=True, text=True, check=True, cwd=ROOT).stdout
+    lines = [ln for ln in out.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert k in d
