@@ -88,12 +88,18 @@ def lidar_sweep(n_rows=64, n_cols=2048, seed=1, elev_deg=(-25.0, 3.0)):
     return pts, lab.reshape(-1).astype(np.int32)
 
 
-def camera_matrix(H, W, fov_scale=0.5625):
-    """KITTI-like P2 @ Tr (3x4, float64) scaled to an HxW image: fx=fy=fov_scale*W, principal point centred.
-    Tr maps velodyne (x fwd, y left, z up) to camera (x right, y down, z fwd) with a small translation."""
+def camera_calibration(H, W, fov_scale=0.5625):
+    """KITTI-like calibration scaled to an HxW image: (P2 3x4, Tr 4x4), float64.  fx=fy=fov_scale*W, principal point
+    centred; Tr maps velodyne (x fwd, y left, z up) to camera (x right, y down, z fwd) with a small translation."""
     fx = fy = fov_scale * W
     P2 = np.array([[fx, 0, W / 2.0, 4.5e1 * W / 1242.0], [0, fy, H / 2.0, -0.3], [0, 0, 1.0, 0.003]], np.float64)
     Tr = np.array([[0, -1, 0, 0.004], [0, 0, -1, -0.076], [1, 0, 0, -0.272], [0, 0, 0, 1]], np.float64)
+    return P2, Tr
+
+
+def camera_matrix(H, W, fov_scale=0.5625):
+    """P2 @ Tr (3x4, float64) of camera_calibration: what parser.py:73-75 hands to mapLidar2Camera."""
+    P2, Tr = camera_calibration(H, W, fov_scale)
     return (P2 @ Tr)[:3]
 
 
