@@ -162,3 +162,53 @@ def test_oracle_equals_live_reference():
     r = knn(*[torch.from_numpy(inp[k]) for k in ("proj_range", "unproj_range", "proj_argmax", "px", "py")]).numpy()
     o, tf = knn_oracle.knn_vote(inp["proj_range"], inp["unproj_range"], inp["proj_argmax"], inp["px"], inp["py"], 5, 5, 1.0, 1.0, 20, return_aux=True)
     assert np.array_equal(o[tf], r[tf])
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
+def test_loss_oracle_equals_reference_modules():
+    """the trainer's loss block (tasks/pmf/trainer.py:188-252, 305-332) composed from the reference's own
+    FocalSoftmaxLoss / Lovasz_softmax / nn.KLDivLoss exactly as the trainer composes them, against oracle/loss_oracle.py:
+    value and gradients w.r.t. both probability maps."""
+    import math
+    from oracle import loss_oracle as lo
+    from oracle.ref_loader import load_reference
+    ref = load_reference()
+    torch.manual_seed(3)
+    C, tau, gamma_w, lam = 20, 0.7, 0.5, 1.0
+    label = torch.randint(0, C, (2, 24, 40))
+    label[0, :6] = 0  # unlabelled rows
+    cls_freq = np.linspace(0.01, 0.2, C)
+    alpha_np = np.log(1 + 1.0 / (cls_freq + 1e-3))
+    alpha_np = alpha_np / alpha_np.max()
+    alpha_np[0] = 0
+    focal = ref.loss.FocalSoftmaxLoss(C, gamma=2, alpha=alpha_np, softmax=False)
+    lovasz = ref.loss.Lovasz_softmax(ignore=0)
+    kl = torch.nn.KLDivLoss(reduction="none")
+
+    def reference_total(lidar_pred, camera_pred):
+        mask = label.gt(0)
+        lp_log = torch.log(lidar_pred.clamp(min=1e-8))
+        pcd_entropy = -(lidar_pred * lp_log).sum(1) / math.log(C)
+        cp_log = torch.log(camera_pred.clamp(min=1e-8))
+        img_entropy = -(camera_pred * cp_log).sum(1) / math.log(C)
+        pcd_conf, img_conf = 1 - pcd_entropy, 1 - img_entropy
+        imp = pcd_conf - img_conf
+        pcd_w = imp.gt(0).float() * imp.abs() * pcd_conf.ge(tau).float()
+        img_w = imp.lt(0).float() * imp.abs() * img_conf.ge(tau).float()
+        per = (kl(lp_log, camera_pred) * img_w.unsqueeze(1)).mean() + (kl(cp_log, lidar_pred) * pcd_w.unsqueeze(1)).mean()
+        return (focal(lidar_pred, label, mask=mask) + lam * lovasz(lidar_pred, label) +
+                focal(camera_pred, label, mask=mask) + lam * lovasz(camera_pred, label) + gamma_w * per)
+
+    # peaked predictions so that a good share of the pixels passes the tau = 0.7 confidence threshold
+    la = (torch.randn(2, C, 24, 40) * 4).requires_grad_(True)
+    lb = (torch.randn(2, C, 24, 40) * 4).requires_grad_(True)
+    r = reference_total(torch.softmax(la, 1), torch.softmax(lb, 1))
+    ga, gb = torch.autograd.grad(r, (la, lb))
+    la2, lb2 = la.detach().clone().requires_grad_(True), lb.detach().clone().requires_grad_(True)
+    o = lo.total_loss(torch.softmax(la2, 1), torch.softmax(lb2, 1), label, torch.from_numpy(alpha_np).float(), C, lam, gamma_w, tau)
+    ga2, gb2 = torch.autograd.grad(o, (la2, lb2))
+    assert abs(float(o) - float(r)) < 1e-5 * max(1.0, abs(float(r)))
+    assert torch.allclose(ga2, ga, rtol=1e-4, atol=1e-7) and torch.allclose(gb2, gb, rtol=1e-4, atol=1e-7)
+    per, pcd_w, img_w = lo.perception_aware_loss(torch.softmax(la, 1).detach(), torch.softmax(lb, 1).detach(), C, tau)
+    assert float(pcd_w.gt(0).float().mean()) > 0.02 and float(img_w.gt(0).float().mean()) > 0.02  # the KL terms are exercised
+    assert torch.allclose(lo.focal_alpha(cls_freq), torch.from_numpy(alpha_np).float(), rtol=1e-6, atol=1e-7)
