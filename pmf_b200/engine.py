@@ -180,7 +180,10 @@ class BNParam:
         self.weight, self.bias = mod.weight, mod.bias
         self.running_mean, self.running_var = mod.running_mean, mod.running_var
         self.nbt = getattr(mod, "num_batches_tracked", None)
-        self.momentum = 0.1 if mod.momentum is None else float(mod.momentum)
+        if mod.momentum is None:
+            raise NotImplementedError("pmf_b200: BatchNorm2d(momentum=None) (cumulative moving average) is not implemented; "
+                                      "the reference uses the default momentum 0.1 everywhere")
+        self.momentum = float(mod.momentum)
         self.eps = float(mod.eps)
         self.c = mod.weight.shape[0]
 
@@ -264,7 +267,9 @@ class WeightCache:
             if e is not None and e["tag"] == tag and (e["dgrad"] is not None or not need_dgrad):
                 return e
         else:
-            tag = (w.data_ptr(), w._version, None if cp.bias is None else (cp.bias.data_ptr(), cp.bias._version), need_dgrad)
+            # re-packed once per pass (Engine): in-place updates through ``.data`` (EMA swaps, manual clipping) do not
+            # bump ``_version``, so a version tag alone would keep convolving with stale packed weights
+            tag = (self.epoch, w.data_ptr(), None if cp.bias is None else cp.bias.data_ptr(), need_dgrad)
             if e is not None and e["tag"] == tag:
                 return e
         dev = w.device

@@ -11,6 +11,7 @@ optimisers, DDP, ``replaceBN`` and ``load_state_dict`` see the tree they expect)
 called: the whole network runs as one autograd.Function over pmf_b200.engine.  There is no CPU path — calling a
 module with CPU tensors raises.
 """
+import contextlib
 import os
 
 import torch
@@ -19,6 +20,12 @@ import torch.nn as nn
 from . import net as G
 from . import _lib as _L
 from .engine import Act, Engine, WeightCache
+
+
+def _on_device(t):
+    """Context manager making t's CUDA device current (launches take the device from the tensors, not from whatever the
+    calling thread had selected).  A no-op for the CPU tensors of the numpy C-ABI model the CPU tests run on."""
+    return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
 
 
 def _require_cuda(*tensors):
@@ -266,10 +273,11 @@ class _PMFFn(torch.autograd.Function):
         if E is None:
             raise RuntimeError("pmf_b200: backward through a forward that was run without gradient recording")
         lidar, camera = ctx.saved_tensors
-        E.st = torch.cuda.current_stream(lidar.device).cuda_stream
-        E.softmax_backward(ctx.ll, lidar, d_lidar)
-        E.softmax_backward(ctx.cl, camera, d_camera)
-        grads = E.run_backward()
+        with _on_device(lidar):  # autograd's worker thread: take the device from the tensors
+            E.st = torch.cuda.current_stream(lidar.device).cuda_stream
+            E.softmax_backward(ctx.ll, lidar, d_lidar)
+            E.softmax_backward(ctx.cl, camera, d_camera)
+            grads = E.run_backward()
         ctx.E = None
         return (None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
@@ -376,7 +384,8 @@ class _PMFGraphFn(torch.autograd.Function):
             raise RuntimeError("pmf_b200: this forward's activations were overwritten by a later forward of the same "
                                "CUDA-graph specialisation; set PMFB_CUDA_GRAPH=0 for call patterns other than "
                                "forward -> backward")
-        return (None, None, None) + r.backward(d_lidar, d_camera)
+        with _on_device(d_lidar):
+            return (None, None, None) + r.backward(d_lidar, d_camera)
 
 
 class PMFNet(nn.Module):
@@ -405,6 +414,15 @@ class PMFNet(nn.Module):
         # honour per-module .eval() on the Dropout2d children (sites whose module is in eval mode are skipped)
         return _DropoutSites(self)
 
+    def _check_modes(self):
+        """BatchNorm mode is taken from the root module: a tree whose BatchNorm children disagree with it (a frozen-BN
+        backbone) would silently normalise with the wrong statistics, so it is refused."""
+        for n, m in self.named_modules():
+            if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.training != self.training:
+                raise NotImplementedError("pmf_b200.PMFNet: BatchNorm module %r is in %s mode but the model is in %s mode; "
+                                          "per-module BatchNorm modes are not supported" %
+                                          (n, "train" if m.training else "eval", "train" if self.training else "eval"))
+
     def _graph_key(self, pcd, img, record, params):
         drop = tuple((n, m.training, m.p) for n, m in self.named_modules() if isinstance(m, nn.Dropout2d))
         ptrs = tuple(p.data_ptr() for p in params) + tuple(b.data_ptr() for b in self.buffers())
@@ -415,6 +433,16 @@ class PMFNet(nn.Module):
         _require_cuda(pcd_feature, img_feature)
         G.check_input_size(img_feature)
         params = [p for _, p in self.named_parameters()]
+        if not params or getattr(self, "_is_replica", False):
+            # nn.DataParallel replicas (trainer.py:41-47, the reference's legacy non-distributed branch) carry no
+            # Parameters and would share this module's caches across threads
+            raise RuntimeError("pmf_b200.PMFNet does not support nn.DataParallel; launch one process per GPU and wrap the "
+                               "model in DistributedDataParallel (tasks/pmf/trainer.py:34-39)")
+        self._check_modes()
+        with _on_device(pcd_feature):
+            return self._forward(pcd_feature, img_feature, params)
+
+    def _forward(self, pcd_feature, img_feature, params):
         record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         use_graph = (os.environ.get("PMFB_CUDA_GRAPH", "1") != "0" and self._dropout_override is None
                      and not torch.cuda.is_current_stream_capturing())
