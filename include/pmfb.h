@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PMFB_ABI_VERSION 2
+#define PMFB_ABI_VERSION 3
 #define PMFB_MAX_TAPS 9
 
 typedef enum {
@@ -148,9 +148,22 @@ int pmfb_nhwc_to_nchw(const pmfb_view* src, int32_t n, int32_t h, int32_t w, int
  * (both multiples of 4, so 3/5/17-channel tensors become TMA-legal):
  *   fwd  [taps][c_out_p][c_in_p]   (pmfb_conv_fwd forward)     if fwd   != NULL
  *   dgrad[taps][c_in_p][c_out_p]   (pmfb_conv_fwd as dgrad)    if dgrad != NULL
- * stem=1: the 7x7x3 stem; taps = kh and the packed input channel is kw_i*c_in + c (c_in_p >= kw*c_in). */
+ * stem=1: the 7x7x3 stem; taps = kh and the packed input channel is kw_i*c_in + c (c_in_p >= kw*c_in).
+ * round_out: 1 = store tf32-rounded values (the default kind::tf32 mode); 0 = keep fp32 (input of pmfb_split_tf32). */
 int pmfb_pack_weight(const float* w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw, int32_t stem,
-                     int32_t c_out_p, int32_t c_in_p, float* fwd, float* dgrad, void* stream);
+                     int32_t c_out_p, int32_t c_in_p, float* fwd, float* dgrad, int32_t round_out, void* stream);
+
+/* Precise mode (3xTF32): split an NHWC fp32 view into tf32-exact parts  hi = rna_tf32(x), lo = rna_tf32(x - hi)  so that
+ *   x*w ~= hi_x*hi_w + hi_x*lo_w + lo_x*hi_w   (three kind::tf32 UMMAs per K step into the same TMEM accumulator; every
+ * product is exact in fp32) recovers the reference's fp32 convolution arithmetic (pmf_net.py / salsanext.py nn.Conv2d) to
+ * ~2^-21 per operand.  The three products are laid out along the GEMM K dimension (channels), zero-padded per part to a
+ * multiple of 32 channels cp = roundup(c, 32), and the implicit-GEMM kernels run unchanged over c_in = 3*cp:
+ *   mode 0: out[..., 3*cp] = [hi | hi | lo]   (activations / gradients: the A operand of pmfb_conv_fwd)
+ *   mode 1: out[..., 3*cp] = [hi | lo | hi]   (packed weights viewed as (1, taps, c_out, c_in))
+ *   mode 2: out[..., c] = hi     mode 3: out[..., c] = lo   (the x / dy operands of the three pmfb_conv_wgrad launches)
+ * out: channel stride 1, element strides o_sn / o_sy / o_sx. */
+int pmfb_split_tf32(const pmfb_view* in, int32_t n, int32_t h, int32_t w, int32_t c, float* out, int64_t o_sn, int64_t o_sy,
+                    int64_t o_sx, int32_t mode, void* stream);
 
 /* packed wgrad [taps][c_in_p][c_out_p] -> OIHW gradient (grad = or += depending on accumulate). */
 int pmfb_unpack_wgrad(const float* packed, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw, int32_t stem,
@@ -227,6 +240,8 @@ typedef struct {
   float* dst;
   float* dst2;
   int32_t c_out, c_in, kh, kw, stem, c_out_p, c_in_p, accumulate;
+  int32_t no_round; /* pack only: 1 = keep fp32 (precise mode, see pmfb_split_tf32) */
+  int32_t reserved;
   int64_t start;
 } pmfb_weight_job;
 int pmfb_weight_jobs(int32_t unpack, const pmfb_weight_job* jobs_device, int32_t n_jobs, int64_t total_work,

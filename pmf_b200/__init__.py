@@ -9,3 +9,19 @@ Everything computes through libpmf_b200.so (include/pmfb.h); there is no CPU pat
 """
 from .modules import EPMFNet, PMFNet, ResidualBasedFusionBlock  # noqa: F401
 from .postproc import KNN, project_scatter  # noqa: F401
+
+
+import contextlib as _contextlib
+
+from ._lib import get_precision, set_precision  # noqa: E402,F401
+
+
+@_contextlib.contextmanager
+def precision(mode):
+    """``with pmf_b200.precision("3xtf32"): ...`` — run the tensor-core convolutions in the precise mode (see
+    pmf_b200/_lib.py; also selectable process-wide with the environment variable PMFB_PRECISION)."""
+    prev = set_precision(mode)
+    try:
+        yield
+    finally:
+        set_precision(prev)

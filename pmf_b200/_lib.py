@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmf_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_TAPS = 9
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
@@ -48,7 +48,8 @@ class WgradDesc(C.Structure):
 
 class WeightJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst2", C.c_void_p), ("c_out", i32), ("c_in", i32), ("kh", i32),
-                ("kw", i32), ("stem", i32), ("c_out_p", i32), ("c_in_p", i32), ("accumulate", i32), ("start", i64)]
+                ("kw", i32), ("stem", i32), ("c_out_p", i32), ("c_in_p", i32), ("accumulate", i32), ("no_round", i32),
+                ("reserved", i32), ("start", i64)]
 
 
 VP = C.POINTER(View)
@@ -64,7 +65,8 @@ _SIGNATURES = {
     "pmfb_memset_zero": ([vp, C.c_size_t, vp], C.c_int),
     "pmfb_pack_input": ([vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, vp, i32, i64, i32, vp], C.c_int),
     "pmfb_nhwc_to_nchw": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
-    "pmfb_pack_weight": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp], C.c_int),
+    "pmfb_pack_weight": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp], C.c_int),
+    "pmfb_split_tf32": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
     "pmfb_unpack_wgrad": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp], C.c_int),
     "pmfb_weight_jobs": ([i32, vp, i32, i64, vp], C.c_int),
     "pmfb_pixel_mask": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
@@ -139,6 +141,30 @@ def call(name, *args):
 def query(name, *args):
     """Entry points that answer a question (return value is the answer, not a status)."""
     return int(getattr(lib(), name)(*args))
+
+
+# ---- precision mode of the tensor-core convolutions (process-wide; pmf_b200.precision(...) switches it)
+#   "tf32"   : kind::tf32 operands (rounded where they are produced), one UMMA per K step — the default, the arithmetic
+#              class of the reference's own GPU path (cuDNN with allow_tf32)
+#   "3xtf32" : hi/lo operand split, three UMMAs per K step into the same TMEM accumulator (pmfb_split_tf32): fp32-class
+#              results, ~3x the tensor time; the parity mode for train-mode (batch-statistics) BatchNorm
+PRECISIONS = ("tf32", "3xtf32")
+_precision = os.environ.get("PMFB_PRECISION", "tf32").lower()
+if _precision not in PRECISIONS:
+    raise PmfbError("PMFB_PRECISION must be one of %s, got %r" % (PRECISIONS, _precision))
+
+
+def get_precision():
+    return _precision
+
+
+def set_precision(mode):
+    global _precision
+    mode = str(mode).lower()
+    if mode not in PRECISIONS:
+        raise ValueError("precision must be one of %s, got %r" % (PRECISIONS, mode))
+    prev, _precision = _precision, mode
+    return prev
 
 
 _inited = False

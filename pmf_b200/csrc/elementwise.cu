@@ -190,7 +190,7 @@ nhwc_to_nchw_kernel(EpiView src, int n, int h, int w, int c, float* __restrict__
 // OIHW -> packed [taps][c_out_p][c_in_p] (fwd) and [taps][c_in_p][c_out_p] (dgrad); pad entries are zero.
 // stem: taps = kh, packed input channel j = kw_i*c_in + c (the horizontally unrolled 7x7 stem).
 __global__ void pack_weight_kernel(const float* __restrict__ w, int c_out, int c_in, int kh, int kw, int stem, int c_out_p,
-                                   int c_in_p, float* __restrict__ fwd, float* __restrict__ dgrad) {
+                                   int c_in_p, float* __restrict__ fwd, float* __restrict__ dgrad, int round_out) {
   const int taps = stem ? kh : kh * kw;
   const long long total = (long long)taps * c_out_p * c_in_p;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -209,7 +209,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int c_out, int c
         v = w[((long long)co * c_in + j) * taps + t];
       }
     }
-    v = round_tf32(v);
+    if (round_out) v = round_tf32(v);
     if (fwd) fwd[i] = v;
     if (dgrad) dgrad[((long long)t * c_in_p + j) * c_out_p + co] = v;
   }
@@ -708,13 +708,13 @@ extern "C" int pmfb_nhwc_to_nchw(const pmfb_view* src, int32_t n, int32_t h, int
 }
 
 extern "C" int pmfb_pack_weight(const float* w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw, int32_t stem,
-                                int32_t c_out_p, int32_t c_in_p, float* fwd, float* dgrad, void* stream) {
+                                int32_t c_out_p, int32_t c_in_p, float* fwd, float* dgrad, int32_t round_out, void* stream) {
   REQ(w && (fwd || dgrad) && c_out > 0 && c_in > 0 && kh > 0 && kw > 0, "pack_weight: bad arguments");
   REQ(c_out_p >= c_out && c_out_p % 4 == 0 && c_in_p % 4 == 0 && c_in_p >= (stem ? kw * c_in : c_in),
       "pack_weight: padded dims (%d,%d) too small or not multiples of 4", c_out_p, c_in_p);
   const long long total = (long long)(stem ? kh : kh * kw) * c_out_p * c_in_p;
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, c_out, c_in, kh, kw, stem, c_out_p, c_in_p, fwd,
-                                                                             dgrad);
+                                                                             dgrad, round_out);
   PMFB_LAUNCH_CHECK("pack_weight_kernel");
   return PMFB_OK;
 }
@@ -727,6 +727,52 @@ extern "C" int pmfb_unpack_wgrad(const float* packed, int32_t c_out, int32_t c_i
   unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, c_out, c_in, kh, kw, stem, c_out_p, c_in_p,
                                                                               grad, accumulate);
   PMFB_LAUNCH_CHECK("unpack_wgrad_kernel");
+  return PMFB_OK;
+}
+
+// ------------------------------------------------------------------------------------ 3xTF32 operand split
+// Precise mode (PMFB_PRECISION=3xtf32): x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi) (|x - hi - lo| <= 2^-22 |x|).
+// A tf32 x tf32 product is exact in the fp32 accumulator, so  x*w ~= hi_x*hi_w + hi_x*lo_w + lo_x*hi_w  restores ~21 bits
+// of operand mantissa with THREE kind::tf32 UMMAs per K step into the same TMEM accumulator.  The three products are laid
+// out along the GEMM K dimension (channels): an activation becomes [hi | hi | lo], a weight [hi | lo | hi], each part
+// zero-padded to a multiple of 32 channels (one TMA slab), and the unmodified implicit-GEMM kernels walk 3x the slabs.
+namespace pmfb {
+__global__ void split_tf32_kernel(EpiView x, int n, int h, int w, int c, int cp, int mode, float* __restrict__ out, long long o_sn,
+                                  long long o_sy, long long o_sx) {
+  const int parts = mode < 2 ? 3 : 1;
+  const int cq = (mode < 2 ? cp : c) >> 2;  // float4 groups per part
+  const long long total = (long long)n * h * w * parts * cq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % cq);
+    long long r = i / cq;
+    const int part = (int)(r % parts);
+    r /= parts;
+    const int xx = (int)(r % w);
+    r /= w;
+    const int yy = (int)(r % h);
+    const int nn = (int)(r / h);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (4 * q < c) v = ld4(x.p + (long long)nn * x.sn + (long long)yy * x.sy + (long long)xx * x.sx + 4 * q);
+    // which half this part holds: mode 0 [hi|hi|lo], mode 1 [hi|lo|hi], mode 2 hi, mode 3 lo
+    const bool lo = (mode == 0 && part == 2) || (mode == 1 && part == 1) || mode == 3;
+    float4 hi4 = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    float4 o = hi4;
+    if (lo) o = make_float4(round_tf32(v.x - hi4.x), round_tf32(v.y - hi4.y), round_tf32(v.z - hi4.z), round_tf32(v.w - hi4.w));
+    *reinterpret_cast<float4*>(out + (long long)nn * o_sn + (long long)yy * o_sy + (long long)xx * o_sx + (long long)part * cp + 4 * q) = o;
+  }
+}
+}  // namespace pmfb
+
+extern "C" int pmfb_split_tf32(const pmfb_view* in, int32_t n, int32_t h, int32_t w, int32_t c, float* out, int64_t o_sn,
+                               int64_t o_sy, int64_t o_sx, int32_t mode, void* stream) {
+  REQ(in && in->ptr && out && c > 0 && c % 4 == 0 && mode >= 0 && mode <= 3, "split_tf32: bad arguments");
+  REQ(((in->sn | in->sy | in->sx | o_sn | o_sy | o_sx) % 4) == 0 && (reinterpret_cast<uintptr_t>(in->ptr) & 15) == 0 &&
+          (reinterpret_cast<uintptr_t>(out) & 15) == 0, "split_tf32: views must be 16-byte aligned with strides multiple of 4");
+  const int cp = (c + 31) & ~31;
+  const long long total = (long long)n * h * w * (mode < 2 ? 3 * (cp / 4) : c / 4);
+  if (total == 0) return PMFB_OK;
+  split_tf32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(in), n, h, w, c, cp, mode, out, o_sn, o_sy, o_sx);
+  PMFB_LAUNCH_CHECK("split_tf32_kernel");
   return PMFB_OK;
 }
 
@@ -913,7 +959,7 @@ weight_jobs_kernel(const pmfb_weight_job* __restrict__ jobs, int n_jobs, long lo
             v = J.src[((long long)co * J.c_in + jj) * taps_p + t];
           }
         }
-        v = round_tf32(v);
+        if (!J.no_round) v = round_tf32(v);
         if (J.dst) J.dst[i] = v;
         if (J.dst2) J.dst2[((long long)t * J.c_in_p + jj) * J.c_out_p + co] = v;
       } else {

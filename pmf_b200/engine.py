@@ -217,6 +217,23 @@ class WeightCache:
         self.always = always
         self.epoch = 0
         self.table = None
+        self.precise = False  # set by the Engine of the pass (pmf_b200._lib precision mode)
+
+    def _split3(self, cp, e, stream):
+        """Precise mode: [hi|lo|hi] split packings of the (un-rounded) packed weights (pmfb_split_tf32 mode 1)."""
+        for key, rows, cols in (("fwd", cp.c_out_p, cp.c_in_p), ("dgrad", cp.c_in_p, cp.c_out_p)):
+            src = e.get(key)
+            if src is None:
+                e[key + "3"] = None
+                continue
+            c3 = 3 * _rup(cols, 32)
+            dst = e.get(key + "3")
+            if dst is None or dst.numel() != cp.taps * rows * c3 or dst.device != src.device:
+                dst = torch.empty(cp.taps * rows * c3, device=src.device, dtype=torch.float32)
+            v = View()
+            v.ptr, v.sn, v.sy, v.sx = src.data_ptr(), 0, rows * cols, cols
+            L.call("pmfb_split_tf32", C.byref(v), 1, cp.taps, rows, cols, dst.data_ptr(), 0, rows * c3, c3, 1, stream)
+            e[key + "3"] = dst
 
     def begin_pass(self):
         self.epoch += 1
@@ -239,6 +256,7 @@ class WeightCache:
             j.src, j.dst, j.dst2 = cp.weight.data_ptr(), e["fwd"].data_ptr(), _p(e["dgrad"])
             j.c_out, j.c_in, j.kh, j.kw, j.stem = cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0
             j.c_out_p, j.c_in_p, j.accumulate, j.start = cp.c_out_p, cp.c_in_p, 0, start
+            j.no_round = 1 if self.precise else 0
             jobs.append(j)
             start += size
         self.table = (_job_table(jobs, device), len(jobs), start, convs, need_dgrad)
@@ -256,6 +274,8 @@ class WeightCache:
                     e["bias"] = b
                 else:
                     e["bias"] = cp.bias.detach()
+            if self.precise:
+                self._split3(cp, e, stream)
             e["tag"] = tag
 
     def get(self, cp, need_dgrad, stream):
@@ -269,7 +289,7 @@ class WeightCache:
         else:
             # re-packed once per pass (Engine): in-place updates through ``.data`` (EMA swaps, manual clipping) do not
             # bump ``_version``, so a version tag alone would keep convolving with stale packed weights
-            tag = (self.epoch, w.data_ptr(), None if cp.bias is None else cp.bias.data_ptr(), need_dgrad)
+            tag = (self.epoch, w.data_ptr(), None if cp.bias is None else cp.bias.data_ptr(), need_dgrad, self.precise)
             if e is not None and e["tag"] == tag:
                 return e
         dev = w.device
@@ -282,7 +302,9 @@ class WeightCache:
         if not wd.is_contiguous():
             wd = wd.contiguous()
         L.call("pmfb_pack_weight", wd.data_ptr(), cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0, cp.c_out_p,
-               cp.c_in_p, e["fwd"].data_ptr(), _p(e["dgrad"]) if need_dgrad else None, stream)
+               cp.c_in_p, e["fwd"].data_ptr(), _p(e["dgrad"]) if need_dgrad else None, 0 if self.precise else 1, stream)
+        if self.precise:
+            self._split3(cp, e, stream)
         if cp.bias is not None:
             if cp.c_out_p != cp.c_out:
                 b = torch.zeros(cp.c_out_p, device=dev, dtype=torch.float32)
@@ -333,6 +355,11 @@ class Engine:
             raise NotImplementedError("pmf_b200: backward is implemented for train-mode (batch-statistics) BatchNorm only; "
                                       "call .train() or run the eval forward under torch.no_grad()")
         self.cache = cache
+        # precision mode of the tensor-core convolutions (pmf_b200._lib): in "3xtf32" nothing is rounded where it is
+        # produced (self.R = 0) and every conv operand is split into tf32 hi/lo parts right before the launch
+        self.precise = L.get_precision() == "3xtf32"
+        self.R = 0 if self.precise else 1
+        self.cache.precise = self.precise
         self.cache.begin_pass()
         self.st = torch.cuda.current_stream(device).cuda_stream
         if self.cache.always and self.cache.table is not None:
@@ -366,7 +393,7 @@ class Engine:
             if v is None:
                 continue
             setattr(e, name, v if isinstance(v, View) else _view(v))
-        e.act, e.round_out = act, rnd
+        e.act, e.round_out = act, (rnd if self.R else 0)
         return e
 
     def pointwise(self, src, dst, **kw):
@@ -401,7 +428,7 @@ class Engine:
         if xd.dtype != torch.float32:
             xd = xd.float()
         L.call("pmfb_pack_input", xd.data_ptr(), xd.stride(0), xd.stride(1), xd.stride(2), xd.stride(3), n, c, h, w, n_shift,
-               out.t.data_ptr(), out.c, out.t.stride(2), 1 if rnd else 0, self.st)
+               out.t.data_ptr(), out.c, out.t.stride(2), self.R if rnd else 0, self.st)
         return out
 
     def to_nchw(self, t, c):
@@ -428,8 +455,25 @@ class Engine:
             s.strides[:] = [2 * sx * 4, sy * 4, 2 * sy * 4, sn * 4]
         return s
 
+    def split(self, t, mode):
+        """pmfb_split_tf32 of an NHWC view (precise mode).  mode 0 / 1: dense (n,h,w,3*roundup(c,32)) [hi|hi|lo] / [hi|lo|hi];
+        mode 2 / 3: dense (n,h,w,c) hi / lo."""
+        n, h, w, c = t.shape
+        co = 3 * _rup(c, 32) if mode < 2 else c
+        out = torch.empty((n, h, w, co), device=self.device, dtype=torch.float32)
+        L.call("pmfb_split_tf32", C.byref(_view(t)), n, h, w, c, out.data_ptr(), out.stride(0), out.stride(1), out.stride(2),
+               mode, self.st)
+        return out
+
     def _conv_launch(self, x_t, c_in, stride2, w_packed, c_out, taps, n, out_h, out_w, out_t, epi, bn_stats=None):
-        """Returns True when ``bn_stats`` (2*c_out fp64 sums, zeroed) was accumulated by the conv's own epilogue."""
+        """Returns True when ``bn_stats`` (2*c_out fp64 sums, zeroed) was accumulated by the conv's own epilogue.
+        Precise mode: ``w_packed`` is the [hi|lo|hi] split packing over 3*roundup(c_in,32) channels and x is split here."""
+        if self.precise:
+            c3 = 3 * _rup(c_in, 32)
+            x_t = self.split(x_t, 0)
+            if stride2:  # the parity view interleaves two pixels along the channel axis: tap_dc counts in split channels
+                taps = [((dc // c_in) * c3, dw, dp, dh, wi) for (dc, dw, dp, dh, wi) in taps]
+            c_in = c3
         d = ConvDesc()
         d.x = self._tma_src(x_t, c_in, stride2)
         d.w = w_packed.data_ptr()
@@ -462,8 +506,8 @@ class Engine:
             oh = (h + 2 * cp.pad - cp.dil * (cp.kh - 1) - 1) // cp.stride + 1
             ow = (w + 2 * cp.pad - cp.dil * (cp.kw - 1) - 1) // cp.stride + 1
         assert tuple(out_t.shape) == (n, oh, ow, cp.c_out_p), (cp.name, tuple(out_t.shape), (n, oh, ow, cp.c_out_p))
-        fused = self._conv_launch(x.t, cp.c_in_p, cp.stride == 2, e["fwd"], cp.c_out_p, cp.fwd_taps(), n, oh, ow, out_t, epi,
-                                  bn_stats=bn_stats)
+        fused = self._conv_launch(x.t, cp.c_in_p, cp.stride == 2, e["fwd3" if self.precise else "fwd"], cp.c_out_p, cp.fwd_taps(),
+                                  n, oh, ow, out_t, epi, bn_stats=bn_stats)
         if self.record:
             self._wg_list.append(cp)
         return fused if bn_stats is not None else e
@@ -504,8 +548,6 @@ class Engine:
             packed = torch.empty(cp.taps * cp.c_in_p * cp.c_out_p, device=self.device, dtype=torch.float32)
             L.call("pmfb_memset_zero", packed.data_ptr(), packed.numel() * 4, self.st)
         d = WgradDesc()
-        d.x = self._tma_src(x.t, cp.c_in_p, cp.stride == 2)
-        d.dy = self._tma_src(d_pre, cp.c_out_p)
         d.c_in, d.c_out, d.n_taps = cp.c_in_p, cp.c_out_p, cp.taps
         for i, (dc, dw, dp, dh, _wi) in enumerate(cp.fwd_taps()):
             d.tap_dc[i], d.tap_dw[i], d.tap_dp[i], d.tap_dh[i] = dc, dw, dp, dh
@@ -516,7 +558,17 @@ class Engine:
         base = ((cp.taps * (_rup(cp.c_in_p, 32) // 32) + 3) // 4) * ((cp.c_out_p + d.n_tile - 1) // d.n_tile)
         d.ksplit = max(1, min(max(1, total_pt // 4), (2 * N_SM + base - 1) // base))
         d.dw = packed.data_ptr()
-        L.call("pmfb_conv_wgrad", C.byref(d), self.st)
+        if self.precise:
+            # dw = x_hi*dy_hi + x_hi*dy_lo + x_lo*dy_hi: three launches accumulating into the same packed gradient
+            x_hi, x_lo = self.split(x.t, 2), self.split(x.t, 3)
+            dy_hi, dy_lo = self.split(d_pre, 2), self.split(d_pre, 3)
+            pairs = ((x_hi, dy_hi), (x_hi, dy_lo), (x_lo, dy_hi))
+        else:
+            pairs = ((x.t, d_pre),)
+        for xa, dya in pairs:
+            d.x = self._tma_src(xa, cp.c_in_p, cp.stride == 2)
+            d.dy = self._tma_src(dya, cp.c_out_p)
+            L.call("pmfb_conv_wgrad", C.byref(d), self.st)
         gw = self._pgrad(cp.name + ".weight", cp.weight)
         if not batched:
             L.call("pmfb_unpack_wgrad", packed.data_ptr(), cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0, cp.c_out_p,
@@ -528,9 +580,10 @@ class Engine:
         assert not cp.stem and cp.c_in_p == cp.c_in
         gx, acc = x.grad_target()
         rnd = 1 if x.round_grad else 0
+        w_dgrad = e["dgrad3" if self.precise else "dgrad"]
         if cp.stride == 1:
             taps = [(0, -dw, 0, -dh, wi) for (_dc, dw, _dp, dh, wi) in cp.fwd_taps()]
-            self._conv_launch(d_pre, cp.c_out_p, False, e["dgrad"], cp.c_in_p, taps, n, h, w, gx,
+            self._conv_launch(d_pre, cp.c_out_p, False, w_dgrad, cp.c_in_p, taps, n, h, w, gx,
                               self._epi(r1=gx if acc else None, rnd=rnd))
             return
         # stride 2: one stride-1 convolution over dy per input parity class
@@ -547,7 +600,7 @@ class Engine:
                     if not acc:
                         self.pointwise(None, sub)
                     continue
-                self._conv_launch(d_pre, cp.c_out_p, False, e["dgrad"], cp.c_in_p, taps, n, h // 2, w // 2, sub,
+                self._conv_launch(d_pre, cp.c_out_p, False, w_dgrad, cp.c_in_p, taps, n, h // 2, w // 2, sub,
                                   self._epi(r1=sub if acc else None, rnd=rnd))
 
     def _bias_grad(self, cp, colsum64):
@@ -601,7 +654,7 @@ class Engine:
         gw, gb = self._pgrad(bn.name + ".weight", bn.weight), self._pgrad(bn.name + ".bias", bn.bias)
         L.call("pmfb_bn_bwd_apply", C.byref(dyv), C.byref(mulv), C.byref(zv), act_z, C.byref(xv), mean.data_ptr(),
                invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), bn.weight.detach().data_ptr(), red.data_ptr(), leaky_x,
-               n, h, w, c, d_pre.data_ptr(), d_pre.stride(0), d_pre.stride(1), d_pre.stride(2), 1, gw.data_ptr(),
+               n, h, w, c, d_pre.data_ptr(), d_pre.stride(0), d_pre.stride(1), d_pre.stride(2), self.R, gw.data_ptr(),
                gb.data_ptr(), _p(cs), _p(g_out), *( (g_out.stride(0), g_out.stride(1), g_out.stride(2)) if g_out is not None
                                                     else (0, 0, 0)), 1 if g_acc else 0, self.st)
         self.param_grads[bn.name + ".weight"] = gw
@@ -643,7 +696,7 @@ class Engine:
                     nv = View()
                     L.call("pmfb_bn_bwd_apply", C.byref(_view(dy)), C.byref(nv), C.byref(_view(y.t)), act, C.byref(nv), None,
                            None, None, None, None, None, 0, n, h, w, c, d_pre.data_ptr(), d_pre.stride(0), d_pre.stride(1),
-                           d_pre.stride(2), 1, None, None, _p(cs), None, 0, 0, 0, 0, self.st)
+                           d_pre.stride(2), self.R, None, None, _p(cs), None, 0, 0, 0, 0, self.st)
                 if cs is not None:
                     self._bias_grad(cp, cs)
                 self._conv_bwd(x, cp, d_pre)
@@ -781,7 +834,7 @@ class Engine:
             alpha, beta = self._bn_eval_affine(self.P.bn(bn))
         rv = _view(r.t) if r is not None else View()
         L.call("pmfb_pixel_scale", C.byref(_view(src_t)), n, h, w, c, _p(pre), act, _p(alpha), _p(beta), C.byref(rv), _p(post),
-               out.t.data_ptr(), out.t.stride(0), out.t.stride(1), out.t.stride(2), 1 if rnd else 0, self.st)
+               out.t.data_ptr(), out.t.stride(0), out.t.stride(1), out.t.stride(2), self.R if rnd else 0, self.st)
         return out
 
     # ------------------------------------------------------------------------------------------ data movement ops
@@ -806,7 +859,7 @@ class Engine:
             out = self.new(n, h // 2, w // 2, c)
         idx = torch.empty((n, h // 2, w // 2, c), device=self.device, dtype=torch.uint8) if (k == 1 and self.record) else None
         L.call("pmfb_pool3s2", k, C.byref(_view(x.t)), n, h, w, c, _p(mask), out.t.data_ptr(), out.t.stride(0), out.t.stride(1),
-               out.t.stride(2), _p(idx), 1, self.st)
+               out.t.stride(2), _p(idx), self.R, self.st)
         if self.record and x.needs_grad:
             def bwd():
                 g = out.grad_read()
@@ -822,13 +875,13 @@ class Engine:
         n, h, w, c4 = x.shape
         c = c4 // 4
         L.call("pmfb_pixel_shuffle", C.byref(_view(x.t)), n, h, w, c, _p(mask), out.t.data_ptr(), out.t.stride(0),
-               out.t.stride(1), out.t.stride(2), 1, self.st)
+               out.t.stride(1), out.t.stride(2), self.R, self.st)
         if self.record and x.needs_grad:
             def bwd():
                 g = out.grad_read()
                 gx, acc = x.grad_target()
                 L.call("pmfb_pixel_shuffle_bwd", C.byref(_view(g)), n, h, w, c, _p(mask), gx.data_ptr(), gx.stride(0),
-                       gx.stride(1), gx.stride(2), 1 if acc else 0, 1 if x.round_grad else 0, self.st)
+                       gx.stride(1), gx.stride(2), 1 if acc else 0, self.R if x.round_grad else 0, self.st)
 
             self.tape.append(bwd)
         return out
@@ -836,7 +889,7 @@ class Engine:
     def upsample2x(self, x, out):
         n, h, w, c = x.shape
         L.call("pmfb_upsample2x", C.byref(_view(x.t)), n, h, w, c, out.t.data_ptr(), out.t.stride(0), out.t.stride(1),
-               out.t.stride(2), 1, self.st)
+               out.t.stride(2), self.R, self.st)
         if self.record and x.needs_grad:
             def bwd():
                 g = out.grad_read()
@@ -853,7 +906,7 @@ class Engine:
         s = self.d64.take(n * c)
         L.call("pmfb_colsum", C.byref(_view(x.t)), n, h, w, c, 1, s.data_ptr(), self.st)
         out = self.new(n, 1, 1, c)
-        L.call("pmfb_d2f", s.data_ptr(), out.t.data_ptr(), n * c, 1.0 / (h * w), 0, 1, self.st)
+        L.call("pmfb_d2f", s.data_ptr(), out.t.data_ptr(), n * c, 1.0 / (h * w), 0, self.R, self.st)
         if self.record and x.needs_grad:
             def bwd():
                 g = out.grad_read()  # (N,1,1,C)
@@ -878,7 +931,7 @@ class Engine:
                 s = self.d64.take(n * c)
                 L.call("pmfb_colsum", C.byref(_view(g)), n, h, w, c, 1, s.data_ptr(), self.st)
                 gv, acc = v.grad_target()
-                L.call("pmfb_d2f", s.data_ptr(), gv.data_ptr(), n * c, 1.0, 1 if acc else 0, 1 if v.round_grad else 0, self.st)
+                L.call("pmfb_d2f", s.data_ptr(), gv.data_ptr(), n * c, 1.0, 1 if acc else 0, self.R if v.round_grad else 0, self.st)
 
             self.tape.append(bwd)
         return out
@@ -902,7 +955,7 @@ class Engine:
         if not dprobs.is_contiguous():
             dprobs = dprobs.contiguous()
         L.call("pmfb_softmax_nchw_bwd", probs.data_ptr(), dprobs.data_ptr(), n, h, w, probs.shape[1], g.data_ptr(), g.stride(0),
-               g.stride(1), g.stride(2), 1, self.st if stream is None else stream)
+               g.stride(1), g.stride(2), self.R, self.st if stream is None else stream)
 
     # ------------------------------------------------------------------------------------------ tape
     def finish_forward(self):

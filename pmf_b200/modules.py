@@ -299,6 +299,7 @@ class _GraphedPMF:
         n, c_pcd, h, w = pcd.shape
         self.shape = (n, c_pcd, h, w)
         self.cache = WeightCache(always=True)
+        self.cache.precise = _L.get_precision() == "3xtf32"
         self.E = None
         self.version = 0
         self.bwd_captured = False
@@ -427,7 +428,7 @@ class PMFNet(nn.Module):
         drop = tuple((n, m.training, m.p) for n, m in self.named_modules() if isinstance(m, nn.Dropout2d))
         ptrs = tuple(p.data_ptr() for p in params) + tuple(b.data_ptr() for b in self.buffers())
         return (tuple(pcd.shape), tuple(img.shape), str(pcd.device), self.training, record, drop, ptrs,
-                tuple(p.requires_grad for p in params))
+                tuple(p.requires_grad for p in params), _L.get_precision())
 
     def forward(self, pcd_feature, img_feature):
         _require_cuda(pcd_feature, img_feature)
@@ -553,6 +554,7 @@ class _GraphedEPMF:
         self.dev = pcd.device
         n, c_pcd, h, w = pcd.shape
         self.cache = WeightCache(always=True)
+        self.cache.precise = _L.get_precision() == "3xtf32"
         self.pool = torch.cuda.graph_pool_handle()
         self.g = torch.cuda.CUDAGraph()
         self.E_in = Engine(G.ModuleParams(mod), self.dev, False, False, WeightCache(), dropout=False)
@@ -613,7 +615,7 @@ class EPMFNet(nn.Module):
             assert False, "invalid input size: {}".format(img_feature.shape)
         use_graph = os.environ.get("PMFB_CUDA_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing()
         if use_graph:
-            key = (tuple(pcd_feature.shape), tuple(img_feature.shape), str(pcd_feature.device),
+            key = (tuple(pcd_feature.shape), tuple(img_feature.shape), str(pcd_feature.device), _L.get_precision(),
                    tuple(p.data_ptr() for p in self.parameters()) + tuple(b.data_ptr() for b in self.buffers()))
             runner = self._graphs.get(key)
             if runner is None and key in self._seen:

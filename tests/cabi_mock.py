@@ -129,7 +129,7 @@ def pmfb_nhwc_to_nchw(src, n, h, w, c, dst, stream):
     _arr(dst, (n, c, h, w), (c * h * w, h * w, w, 1))[...] = np.transpose(v, (0, 3, 1, 2))
 
 
-def pmfb_pack_weight(wp, c_out, c_in, kh, kw, stem, c_out_p, c_in_p, fwd, dgrad, stream):
+def pmfb_pack_weight(wp, c_out, c_in, kh, kw, stem, c_out_p, c_in_p, fwd, dgrad, round_out, stream):
     w = _arr(wp, (c_out, c_in, kh, kw), (c_in * kh * kw, kh * kw, kw, 1))
     taps = kh if stem else kh * kw
     pk = np.zeros((taps, c_out_p, c_in_p), np.float32)
@@ -139,7 +139,8 @@ def pmfb_pack_weight(wp, c_out, c_in, kh, kw, stem, c_out_p, c_in_p, fwd, dgrad,
                 pk[ki, :c_out, kj * c_in:(kj + 1) * c_in] = w[:, :, ki, kj]
     else:
         pk[:, :c_out, :c_in] = np.transpose(w.reshape(c_out, c_in, taps), (2, 0, 1))
-    pk = rtf32(pk)
+    if round_out:
+        pk = rtf32(pk)
     if fwd:
         _arr(fwd, pk.shape, (c_out_p * c_in_p, c_in_p, 1))[...] = pk
     if dgrad:
@@ -366,6 +367,31 @@ def pmfb_softmax_nchw_bwd(p, dp, n, h, w, c, dz, d_sn, d_sy, d_sx, rnd, stream):
     o[..., c:] = 0
 
 
+def _trunc_tf32(x):
+    """What the tensor core does with an fp32 bit pattern fed to kind::tf32: the low 13 mantissa bits are ignored."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if EXACT:
+        return x
+    return (x.view(np.int32) & ~np.int32(0x1FFF)).view(np.float32)
+
+
+def pmfb_split_tf32(inp, n, h, w, c, out, o_sn, o_sy, o_sx, mode, stream):
+    x = np.array(_view(_deref(inp), n, h, w, c), dtype=np.float32)
+    b = x.view(np.int32)
+    hi = ((b + 0x1000) & ~np.int32(0x1FFF)).view(np.float32)  # always a real rna_tf32 (also in EXACT mode)
+    d = (x - hi).astype(np.float32)
+    lo = ((d.view(np.int32) + 0x1000) & ~np.int32(0x1FFF)).view(np.float32)
+    if mode >= 2:
+        _arr(out, (n, h, w, c), (o_sn, o_sy, o_sx, 1))[...] = hi if mode == 2 else lo
+        return
+    cp = (c + 31) // 32 * 32
+    o = _arr(out, (n, h, w, 3 * cp), (o_sn, o_sy, o_sx, 1))
+    o[...] = 0
+    parts = (hi, hi, lo) if mode == 0 else (hi, lo, hi)
+    for k, part in enumerate(parts):
+        o[..., k * cp:k * cp + c] = part
+
+
 def _tma_gather(src, c_lo, c_n, x0_of, tile):
     """Zero-filled read of channels [c_lo, c_lo+c_n) for all (n, y, x) of the logical output grid at tap offset."""
     raise NotImplementedError
@@ -403,7 +429,7 @@ def pmfb_conv_fwd(dp_, stream):
     for t in range(d.n_taps):
         wi = d.tap_wi[t] if d.use_tap_wi else t
         a = _tap_read(X, d.tap_dc[t], d.c_in, d.tap_dw[t], d.tap_dp[t], d.tap_dh[t], d.out_h, d.out_w)
-        acc += (a.reshape(-1, d.c_in) @ Wp[wi].T).reshape(acc.shape)
+        acc += (_trunc_tf32(a).reshape(-1, d.c_in) @ _trunc_tf32(Wp[wi]).T).reshape(acc.shape)
     res = _epilogue(d.epi, acc, d.n_batch, d.out_h, d.out_w, d.c_out)
     _arr(d.out, acc.shape, (d.o_sn, d.o_sy, d.o_sx, 1))[...] = res
     if d.bn_stats:  # fused BatchNorm statistics of the epilogue result (pmfb_bn_stats contract)
@@ -430,11 +456,11 @@ def pmfb_conv_wgrad(dp_, stream):
     d = _deref(dp_)
     X = _src5(d.x)
     DY = _src5(d.dy)
-    dy = _tap_read(DY, 0, d.c_out, 0, 0, 0, d.out_h, d.out_w).reshape(-1, d.c_out)
+    dy = _trunc_tf32(_tap_read(DY, 0, d.c_out, 0, 0, 0, d.out_h, d.out_w)).reshape(-1, d.c_out)
     dw = _arr(d.dw, (d.n_taps, d.c_in, d.c_out), (d.c_in * d.c_out, d.c_out, 1))
     for t in range(d.n_taps):
         a = _tap_read(X, d.tap_dc[t], d.c_in, d.tap_dw[t], d.tap_dp[t], d.tap_dh[t], d.out_h, d.out_w).reshape(-1, d.c_in)
-        dw[t] += a.T @ dy
+        dw[t] += _trunc_tf32(a).T @ dy
 
 
 def pmfb_pixel_mask(x, n, h, w, c, mask, stream):

@@ -237,3 +237,35 @@ def test_epmf_rejects_training_and_bad_sizes():
     m = M.EPMFNet(5, 3, 20, 32, False, "resnet34")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 5, 32, 32), torch.zeros(1, 3, 32, 32))
+
+
+def test_precise_mode_3xtf32_recovers_fp32_on_the_truncating_model(mock):
+    """PMFB_PRECISION=3xtf32 wiring: on the tf32 model of the library (the tensor core ignores the low 13 operand mantissa
+    bits) the default mode deviates from the fp32 oracle by operand rounding (~1e-3 on this fixture) while the precise mode
+    -- nothing rounded where it is produced, every conv operand split into [hi|hi|lo] x [hi|lo|hi] over 3x the channels,
+    three wgrad launches -- matches it like exact arithmetic does, forward and gradients, stride-2 and stem included."""
+    import pmf_b200
+    case = synth.PMF_CASES[0]
+    res = {}
+    for mode in ("tf32", "3xtf32"):
+        m, sd, pcd, img = _pmf_case(case["backbone"], case["nclasses"], case["B"], case["H"], case["W"], case["seed"])
+        m.train()
+        m._dropout_override = False
+        with pmf_b200.precision(mode):
+            lid, cam = M._PMFFn.apply(m, True, pcd, img, *[p for _, p in m.named_parameters()])
+            wl, wc = synth.pmf_loss_weights(case)
+            ((lid * wl).sum() + (cam * wc).sum()).backward()
+        params = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+                  for k, v in sd.items()}
+        rl, rc = po.pmf_forward(params, pcd, img, case["backbone"], train=True)
+        ((rl * wl).sum() + (rc * wc).sum()).backward()
+        errs = []
+        for n, p in m.named_parameters():
+            wname = n.rsplit(".", 1)[0] + ".weight"
+            errs.append(_l2_err(p.grad, params[n].grad, 1e-2 * float(params[wname].grad.double().norm())))
+        res[mode] = (max(_maxrel(lid.detach(), rl.detach()), _maxrel(cam.detach(), rc.detach())), float(np.median(errs)))
+    # gradients: the same 2e-2 relative-L2 bar the exact-arithmetic wiring test uses (batch-statistics BN on random weights
+    # amplifies even fp32 summation-order noise); the default mode sits at ~0.5 on this fixture
+    assert res["3xtf32"][0] < 1e-4 and res["3xtf32"][1] < 2e-2, res
+    assert res["tf32"][1] > 10 * res["3xtf32"][1], res
+    assert res["tf32"][0] > 10 * res["3xtf32"][0], res  # the model really does lose the low operand bits in the default mode

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--eval", action="store_true", help="profile an eval-mode forward instead of a training step")
+    ap.add_argument("--loss", default="fused", choices=["fused", "torch"])
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(1)
@@ -45,9 +46,13 @@ def main():
                                              list(model.camera_stream_encoder.parameters()) +
                                              list(model.camera_stream_decoder.parameters()))
 
+        from pmf_b200.loss import TrainerLoss
+        crit = TrainerLoss(bench.NCLASSES, None, bench.LAMBDA, bench.GAMMA, bench.TAU,
+                           impl="auto" if a.loss == "fused" else "torch").to(dev)
+
         def step():
             lid, cam = model(x[:, 0:5], x[:, 5:8])
-            loss = bench.nll_loss(lid, cam, y)
+            loss = crit(lid, cam, y)
             opt_a.zero_grad(set_to_none=True)
             opt_b.zero_grad(set_to_none=True)
             loss.backward()
