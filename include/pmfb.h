@@ -284,6 +284,37 @@ int pmfb_softmax_nchw_bwd(const float* p, const float* dp, int32_t n, int32_t h,
                           int64_t d_sn, int64_t d_sy, int64_t d_sx, int32_t round_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused loss head: the loss block tasks/pmf/trainer.py:305-332 applies to the two softmax maps
+ * ------------------------------------------------------------------------------------------- */
+
+/* One pass over the two dense NCHW probability maps (n, c, h, w) and the int64 labels (n, h, w):
+ *   focal:       -(1 - p_t)^focal_gamma * log(clamp(p_t, 1e-6)) * alpha[t] summed over the pixels with label > 0
+ *                (pc_processor/loss/focal_softmax.py:28-62 with softmax=False, mask = label > 0), per head;
+ *   perception:  entropy -> confidence = 1 - H(p)/log c per head; guide weights 1[d>0]|d|1[conf>=tau] with
+ *                d = conf_lidar - conf_camera; KLDivLoss(reduction="none")(log p_lidar, p_camera) * w_camera and the
+ *                reverse direction, summed over all elements (trainer.py:231-252, 305-319).
+ * sums (8 doubles, caller zeroes): [0] focal lidar, [1] focal camera, [2] number of labelled pixels, [3] KL numerator of
+ * loss_per_pcd, [4] of loss_per_img, [5] sum of lidar entropies, [6] sum of camera entropies.  The loss value is
+ *   w_focal * (sums[0] + sums[1]) / sums[2] + w_per * (sums[3] + sums[4]) / (n*c*h*w).
+ * d_lidar / d_camera (dense NCHW, may both be NULL): WRITTEN with the gradient of exactly that value with respect to the
+ * two maps (through the logs, the entropies and the guide weights, like autograd on the reference's expressions). */
+int pmfb_loss_head(const float* p_lidar, const float* p_camera, const int64_t* label, int32_t n, int32_t c, int32_t h,
+                   int32_t w, const float* alpha, float focal_gamma, float tau, float w_focal, float w_per, float* d_lidar,
+                   float* d_camera, double* sums, void* stream);
+
+/* Lovasz-softmax (pc_processor/loss/lovasz_softmax.py:55-145; classes="present", per_image=False, pixels whose label ==
+ * ignore dropped) of one or two heads (probs1 may be NULL) in one pipeline: compaction of the labelled pixels, one LSD
+ * radix sort of (head, class, descending |fg - p|, pixel) keys, foreground scan, Jaccard gradient, per-class losses.
+ * loss_out[head] += mean over the present classes of the class losses (doubles, caller zeroes).
+ * d_probs0 / d_probs1 (dense NCHW, may be NULL): ACCUMULATED (+=) with grad_scale * d loss / d probs.
+ * workspace: pmfb_lovasz_workspace_bytes(n*h*w, c, heads) bytes, 256-byte aligned, contents undefined on entry; nothing is
+ * read back by the host (grids are sized for the worst case and take the labelled-pixel count from device memory). */
+size_t pmfb_lovasz_workspace_bytes(int64_t n_pixels, int32_t c, int32_t n_heads);
+int pmfb_lovasz(const float* probs0, const float* probs1, const int64_t* label, int32_t n, int32_t c, int32_t h, int32_t w,
+                int32_t ignore, float grad_scale, float* d_probs0, float* d_probs1, double* loss_out, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Post-processing / pre-processing
  * ------------------------------------------------------------------------------------------- */
 

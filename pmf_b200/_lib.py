@@ -88,6 +88,9 @@ _SIGNATURES = {
     "pmfb_upsample2x_bwd": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
     "pmfb_softmax_nchw": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
     "pmfb_softmax_nchw_bwd": ([vp, vp, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
+    "pmfb_loss_head": ([vp, vp, vp, i32, i32, i32, i32, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp], C.c_int),
+    "pmfb_lovasz_workspace_bytes": ([i64, i32, i32], C.c_size_t),
+    "pmfb_lovasz": ([vp, vp, vp, i32, i32, i32, i32, i32, C.c_float, vp, vp, vp, vp, C.c_size_t, vp], C.c_int),
     "pmfb_knn_vote": ([vp, vp, i32, i32, vp, vp, vp, i64, vp, i32, i32, C.c_float, i32, vp, vp], C.c_int),
     "pmfb_project_scatter": ([vp, vp, i64, C.POINTER(C.c_double), i32, i32, vp, vp, vp, vp, vp, vp, vp, vp], C.c_int),
 }

@@ -13,6 +13,7 @@ Reference semantics (paths relative to the reference tree):
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -317,6 +318,18 @@ class WeightCache:
         return e
 
 
+_side_streams = {}
+
+
+def _side_stream(device):
+    """One auxiliary CUDA stream per device for the weight-gradient kernels (see Engine._conv_bwd)."""
+    key = str(device)
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 class _Scratch:
     """Bump allocator over one zero-initialised buffer (fp64 reduction cells) or an uninitialised fp32 one."""
 
@@ -375,6 +388,12 @@ class Engine:
         self.param_grads = {}
         self.flat_views = None  # graph mode: {param name: view into one flat gradient buffer}
         self.nbt_list = []
+        # backward: the wgrad kernels (tensor pipe + ~2.6 TB/s) run on a side stream next to the BatchNorm-backward /
+        # dgrad chain of the following layers (HBM-bound elementwise kernels co-reside with a wgrad CTA on an SM); the
+        # operands they read are kept alive until the streams join at the end of run_backward
+        self.side = None
+        self._side_keep = []
+        self.use_side = os.environ.get("PMFB_WGRAD_STREAM", "1") != "0" and str(device).startswith("cuda")
 
     # ------------------------------------------------------------------------------------------ helpers
     def _pgrad(self, name, like):
@@ -558,6 +577,15 @@ class Engine:
         base = ((cp.taps * (_rup(cp.c_in_p, 32) // 32) + 3) // 4) * ((cp.c_out_p + d.n_tile - 1) // d.n_tile)
         d.ksplit = max(1, min(max(1, total_pt // 4), (2 * N_SM + base - 1) // base))
         d.dw = packed.data_ptr()
+        main_st = self.st
+        if self.use_side:
+            if self.side is None:
+                self.side = _side_stream(self.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))   # d_pre (and, the first time, the zeroed arena) are ready
+            self.side.wait_event(ev)
+            self.st = self.side.cuda_stream
+            self._side_keep.append((x.t, d_pre, packed))
         if self.precise:
             # dw = x_hi*dy_hi + x_hi*dy_lo + x_lo*dy_hi: three launches accumulating into the same packed gradient
             x_hi, x_lo = self.split(x.t, 2), self.split(x.t, 3)
@@ -569,10 +597,13 @@ class Engine:
             d.x = self._tma_src(xa, cp.c_in_p, cp.stride == 2)
             d.dy = self._tma_src(dya, cp.c_out_p)
             L.call("pmfb_conv_wgrad", C.byref(d), self.st)
+            if self.use_side:
+                self._side_keep.append((xa, dya))
         gw = self._pgrad(cp.name + ".weight", cp.weight)
         if not batched:
             L.call("pmfb_unpack_wgrad", packed.data_ptr(), cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0, cp.c_out_p,
                    cp.c_in_p, gw.data_ptr(), 0, self.st)
+        self.st = main_st
         self.param_grads[cp.name + ".weight"] = gw
         # ---- dgrad
         if not x.needs_grad:
@@ -963,6 +994,14 @@ class Engine:
             torch._foreach_add_(self.nbt_list, 1)  # num_batches_tracked bookkeeping (host-side plumbing)
             self.nbt_list = []
 
+    def join_side(self):
+        """The main stream waits for every wgrad launched on the side stream so far; their operands may be released."""
+        if self.side is not None and self._side_keep:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+        self._side_keep = []
+
     def run_backward(self):
         self.st = torch.cuda.current_stream(self.device).cuda_stream
         self.d64 = _Scratch(torch.float64, 1 << 17, self.device, self.st, zero=True)
@@ -971,6 +1010,7 @@ class Engine:
             L.call("pmfb_memset_zero", self._wg_arena.data_ptr(), self._wg_arena.numel() * 4, self.st)
         for fn in reversed(self.tape):
             fn()
+        self.join_side()
         if self._unpack_table is not None:
             tab, n, total = self._unpack_table
             L.call("pmfb_weight_jobs", 1, tab.data_ptr(), n, total, self.st)

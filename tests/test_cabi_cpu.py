@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_prototypes():
     h = open(os.path.join(ROOT, "include", "pmfb.h")).read()
     h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
-    return re.findall(r"(?:int|const char\*)\s+(pmfb_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S)
+    return re.findall(r"(?:int|size_t|const char\*)\s+(pmfb_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S)
 
 
 def test_library_exports_every_declared_symbol():
