@@ -476,6 +476,19 @@ def run_ours(args):
         ms_torch_loss = timed(lambda: step(d_feat, d_label), max(3, args.steps // 4)) / max(3, args.steps // 4)
         loss_sel["impl"] = args.loss
 
+    # exposed (non-overlapped) gradient all-reduce: the same step with DDP's synchronisation switched off
+    ddp_info = None
+    if world > 1:
+        def step_nosync():
+            with net.no_sync():
+                step(d_feat, d_label)
+        step_nosync()
+        k_ns = max(3, args.steps // 2)
+        ms_ns = timed(step_nosync, k_ns) / k_ns
+        ddp_info = {"ms_per_step_no_sync": ms_ns, "exposed_allreduce_ms": ms / args.steps - ms_ns,
+                    "grad_bytes": sum(p.numel() for p in model.parameters()) * 4,
+                    "backward_segments": int(os.environ.get("PMFB_BWD_SEGMENTS", "4"))}
+
     frames = B * world * args.steps
     value = frames / (ms * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
@@ -539,7 +552,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": h_feat.numel() * 4 + h_label.numel() * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "step_tflops": STEP_KFLOP_PER_PX * 1e3 * H * W * B / (ms / args.steps * 1e-3) / 1e12,
-            "ms_per_step_with_torch_loss_block": ms_torch_loss,
+            "ms_per_step_with_torch_loss_block": ms_torch_loss, "ddp": ddp_info,
             "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "common_grid_64x2048": grid2, "extras": extras}
     print(json.dumps(line), flush=True)
     if world > 1:

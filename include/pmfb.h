@@ -328,6 +328,27 @@ int pmfb_knn_vote(const float* proj_range, const int64_t* proj_argmax, int32_t h
                   const float* inv_gauss, int32_t search, int32_t knn, float cutoff, int32_t nclasses,
                   int64_t* out, void* stream);
 
+/* The same vote for ANY NUMBER OF FRAMES in one launch (the reference is un-batched, knn.py:56-59): the
+ * range / argmax images are (n_frames, h, w), the point arrays are the frames' points concatenated, point_offsets
+ * (n_frames + 1 int64, device memory) gives each frame's slice.  One thread per point, top-k in registers (knn <= 8). */
+int pmfb_knn_vote_batched(const float* proj_range, const int64_t* proj_argmax, int32_t n_frames, int32_t h, int32_t w,
+                          const float* unproj_range, const int64_t* px, const int64_t* py, const int64_t* point_offsets,
+                          int64_t n_points, const float* inv_gauss, int32_t search, int32_t knn, float cutoff,
+                          int32_t nclasses, int64_t* out, void* stream);
+
+/* Inference tail on the device (tasks/pmf_eval_semantickitti/infer.py:107-146, tasks/pmf_eval_nuscenes/infer.py:18-38):
+ * pmfb_argmax_nchw:   label[b,y,x] = argmax_c probs[b,c,y0+y,x0+x] (first maximum, like torch.argmax) over the crop
+ *                     window (y0, x0, out_h, out_w) of a dense NCHW map; conf (may be NULL) = the winning probability.
+ * pmfb_lut_remap:     out[i] = lut[labels[i]] (class_map_lut_inv: training ids -> dataset ids; out-of-range -> 0).
+ * pmfb_merge_cameras: per point the prediction of the camera with the highest confidence (ties: lowest camera; no
+ *                     camera: -1).  Inputs are the cameras' per-point arrays concatenated (point index int64, confidence
+ *                     f32, prediction int64, camera id int32 in [0,8)); scratch: pc_size uint64. */
+int pmfb_argmax_nchw(const float* probs, int32_t n, int32_t c, int32_t h, int32_t w, int32_t y0, int32_t x0, int32_t out_h,
+                     int32_t out_w, int64_t* label, float* conf, void* stream);
+int pmfb_lut_remap(const int64_t* labels, int64_t n, const int32_t* lut, int32_t lut_size, int32_t* out, void* stream);
+int pmfb_merge_cameras(const int64_t* point_idx, const float* conf, const int64_t* argmax, const int32_t* cam,
+                       int64_t n_entries, int64_t pc_size, uint64_t* scratch, int64_t* merged, void* stream);
+
 /* Perspective projection + scatter (parser.py:209-227, perspective_view_loader.py:87-131):
  * q = M*[x y z 1]^T in float64, keep x>0.5 and 0<u<W, 0<v<H, truncate to (row,col); per pixel the point
  * with the HIGHEST index wins (numpy fancy-assignment order).  Two passes over `winner` (int32 H*W,

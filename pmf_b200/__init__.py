@@ -8,7 +8,7 @@ Public surface (mirrors the reference's names):
 Everything computes through libpmf_b200.so (include/pmfb.h); there is no CPU path.
 """
 from .modules import EPMFNet, PMFNet, ResidualBasedFusionBlock  # noqa: F401
-from .postproc import KNN, project_scatter  # noqa: F401
+from .postproc import KNN, InferenceTail, argmax_nchw, knn_batched, lut_remap, merge_cameras, project_scatter  # noqa: F401
 
 
 import contextlib as _contextlib

@@ -92,6 +92,10 @@ _SIGNATURES = {
     "pmfb_lovasz_workspace_bytes": ([i64, i32, i32], C.c_size_t),
     "pmfb_lovasz": ([vp, vp, vp, i32, i32, i32, i32, i32, C.c_float, vp, vp, vp, vp, C.c_size_t, vp], C.c_int),
     "pmfb_knn_vote": ([vp, vp, i32, i32, vp, vp, vp, i64, vp, i32, i32, C.c_float, i32, vp, vp], C.c_int),
+    "pmfb_knn_vote_batched": ([vp, vp, i32, i32, i32, vp, vp, vp, vp, i64, vp, i32, i32, C.c_float, i32, vp, vp], C.c_int),
+    "pmfb_argmax_nchw": ([vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp], C.c_int),
+    "pmfb_lut_remap": ([vp, i64, vp, i32, vp, vp], C.c_int),
+    "pmfb_merge_cameras": ([vp, vp, vp, vp, i64, i64, vp, vp, vp], C.c_int),
     "pmfb_project_scatter": ([vp, vp, i64, C.POINTER(C.c_double), i32, i32, vp, vp, vp, vp, vp, vp, vp, vp], C.c_int),
 }
 
@@ -130,7 +134,7 @@ def last_error():
 def check(rc, what):
     if rc != 0:
         msg = last_error()
-        if what == "pmfb_knn_vote" and "odd number" in msg:
+        if what in ("pmfb_knn_vote", "pmfb_knn_vote_batched") and "odd number" in msg:
             raise ValueError(msg)  # knn.py:73-74 raises ValueError
         raise PmfbError("%s failed (%d): %s" % (what, rc, msg))
 

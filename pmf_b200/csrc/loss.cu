@@ -90,14 +90,19 @@ loss_head_kernel(const float* __restrict__ pl, const float* __restrict__ pc, con
     // pass 1: entropies (trainer.py:305-319) and the two KL sums (trainer.py:247-250; KLDivLoss(reduction="none")(log a, b) =
     // xlogy(b, b) - b * log a)
     float sl = 0.f, sc = 0.f, A = 0.f, Bk = 0.f;
+    float lgl[CMAX], lgc[CMAX];  // log(clamp(p, 1e-8)); equals log p unless p < 1e-8 (then xlogy's log p is taken separately)
 #pragma unroll
     for (int k = 0; k < CMAX; ++k)
       if (k < c) {
         const float ll = logf(fmaxf(vl[k], 1e-8f)), lc = logf(fmaxf(vc[k], 1e-8f));
+        lgl[k] = ll;
+        lgc[k] = lc;
         sl += vl[k] * ll;
         sc += vc[k] * lc;
-        A += (vc[k] > 0.f ? vc[k] * logf(vc[k]) : 0.f) - vc[k] * ll;   // KL term pulling the LiDAR head towards the camera head
-        Bk += (vl[k] > 0.f ? vl[k] * logf(vl[k]) : 0.f) - vl[k] * lc;
+        const float rl = vl[k] >= 1e-8f ? ll : (vl[k] > 0.f ? logf(vl[k]) : 0.f);  // log p of xlogy(p, p)
+        const float rc = vc[k] >= 1e-8f ? lc : (vc[k] > 0.f ? logf(vc[k]) : 0.f);
+        A += vc[k] * rc - vc[k] * ll;   // KL term pulling the LiDAR head towards the camera head
+        Bk += vl[k] * rl - vl[k] * lc;
       }
     const float conf_l = 1.f + sl * inv_logc, conf_c = 1.f + sc * inv_logc;  // 1 - entropy / log C
     const float imp = conf_l - conf_c;
@@ -121,16 +126,18 @@ loss_head_kernel(const float* __restrict__ pl, const float* __restrict__ pc, con
       for (int k = 0; k < CMAX; ++k)
         if (k < c) {
           const float p = vl[k], q = vc[k];
-          const float ll = logf(fmaxf(p, 1e-8f)), lc = logf(fmaxf(q, 1e-8f));
+          const float ll = lgl[k], lc = lgc[k];
           const float cl_p = p >= 1e-8f ? 1.f : 0.f, cl_q = q >= 1e-8f ? 1.f : 0.f;  // d log(clamp(x)) / dx = [x >= 1e-8] / x
+          const float rl1 = p >= 1e-8f ? ll + 1.f : (p > 0.f ? logf(p) + 1.f : 0.f);  // d xlogy(p, p) / dp = log p + 1
+          const float rc1 = q >= 1e-8f ? lc + 1.f : (q > 0.f ? logf(q) + 1.f : 0.f);
           // perception-aware terms
-          float g_l = w_c * (-q * cl_p / fmaxf(p, 1e-8f)) + w_l * ((p > 0.f ? logf(p) + 1.f : 0.f) - lc) + dimp * (ll + cl_p) * inv_logc;
-          float g_c = w_l * (-p * cl_q / fmaxf(q, 1e-8f)) + w_c * ((q > 0.f ? logf(q) + 1.f : 0.f) - ll) - dimp * (lc + cl_q) * inv_logc;
+          float g_l = w_c * (-q * cl_p / fmaxf(p, 1e-8f)) + w_l * (rl1 - lc) + dimp * (ll + cl_p) * inv_logc;
+          float g_c = w_l * (-p * cl_q / fmaxf(q, 1e-8f)) + w_c * (rc1 - ll) - dimp * (lc + cl_q) * inv_logc;
           g_l *= per_scale;
           g_c *= per_scale;
           if (lab && k == (int)t) {  // focal: -(1 - p)^g * log(clamp(p, 1e-6)) * alpha[t], mean over the labelled pixels
             const float pt_l = p, pt_c = q;
-            const float lg_l = logf(fmaxf(pt_l, 1e-6f)), lg_c = logf(fmaxf(pt_c, 1e-6f));
+            const float lg_l = pt_l >= 1e-6f ? ll : logf(1e-6f), lg_c = pt_c >= 1e-6f ? lc : logf(1e-6f);
             const float om_l = 1.f - pt_l, om_c = 1.f - pt_c;
             const float pw_l = focal_gamma == 2.f ? om_l * om_l : powf(om_l, focal_gamma);
             const float pw_c = focal_gamma == 2.f ? om_c * om_c : powf(om_c, focal_gamma);
@@ -255,27 +262,23 @@ radix_hist_kernel(const unsigned long long* __restrict__ keys, const LovCtl* __r
   hist[(long long)threadIdx.x * nblk_max + blockIdx.x] = s_h[threadIdx.x];
 }
 
-// exclusive scan of the (digit-major) histogram over the blocks in use: one block of 1024 threads walks the logical
-// sequence (digit, block) with a running carry.
+// exclusive scan of every digit's row of the (digit-major) histogram over the blocks in use: one block of 1024 threads per
+// digit walks its row with a running carry and leaves the row total in digit_total[digit]; the 256 totals are scanned in
+// the prologue of the scatter kernel.
 __global__ void __launch_bounds__(1024)
-radix_scan_kernel(unsigned int* __restrict__ hist, const LovCtl* __restrict__ ctl, int per_pixel, int nblk_max) {
+radix_scan_kernel(unsigned int* __restrict__ hist, const LovCtl* __restrict__ ctl, int per_pixel, int nblk_max,
+                  unsigned int* __restrict__ digit_total) {
   const long long N = (long long)ctl->n_valid * per_pixel;
   const int nblk = (int)((N + kTile - 1) / kTile);
-  const long long total = 256LL * nblk;
+  unsigned int* row = hist + (long long)blockIdx.x * nblk_max;
   __shared__ unsigned int s_w[32];
   __shared__ unsigned int s_carry;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long base = 0; base < total; base += 1024) {
-    const long long e = base + threadIdx.x;
-    unsigned int v = 0;
-    long long addr = 0;
-    if (e < total) {
-      const int d = (int)(e / nblk), b = (int)(e - (long long)d * nblk);
-      addr = (long long)d * nblk_max + b;
-      v = hist[addr];
-    }
+  for (int base = 0; base < nblk; base += 1024) {
+    const int e = base + threadIdx.x;
+    const unsigned int v = e < nblk ? row[e] : 0u;
     unsigned int x = v;  // inclusive warp scan
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -295,25 +298,41 @@ radix_scan_kernel(unsigned int* __restrict__ hist, const LovCtl* __restrict__ ct
     }
     __syncthreads();
     const unsigned int carry = s_carry;
-    if (e < total) hist[addr] = carry + s_w[warp] + x - v;
+    if (e < nblk) row[e] = carry + s_w[warp] + x - v;
     __syncthreads();
     if (threadIdx.x == 1023) s_carry = carry + s_w[31] + x;
     __syncthreads();
   }
+  if (threadIdx.x == 0) digit_total[blockIdx.x] = s_carry;
 }
 
 // stable scatter: 16 rounds of 256 keys; per round the lanes of a warp holding the same digit are ranked with match_any,
 // the warps are chained through shared memory, and the block's running digit bases advance.
 __global__ void __launch_bounds__(kRadixThreads)
 radix_scatter_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, const LovCtl* __restrict__ ctl,
-                     int per_pixel, int shift, const unsigned int* __restrict__ hist, int nblk_max) {
+                     int per_pixel, int shift, const unsigned int* __restrict__ hist, int nblk_max,
+                     const unsigned int* __restrict__ digit_total) {
   const long long N = (long long)ctl->n_valid * per_pixel;
   const long long start = (long long)blockIdx.x * kTile;
   if (start >= N) return;
   __shared__ unsigned int s_base[256];
   __shared__ unsigned int s_cnt[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  s_base[threadIdx.x] = hist[(long long)threadIdx.x * nblk_max + blockIdx.x];
+  {  // exclusive scan of the 256 digit totals (thread = digit) + this block's offset inside the digit's row
+    __shared__ unsigned int s_tw[8];
+    const unsigned int v = digit_total[threadIdx.x];
+    unsigned int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_tw[warp] = x;
+    __syncthreads();
+    unsigned int pre = 0;
+    for (int w = 0; w < warp; ++w) pre += s_tw[w];
+    s_base[threadIdx.x] = pre + x - v + hist[(long long)threadIdx.x * nblk_max + blockIdx.x];
+  }
   for (int r = 0; r < kTile / kRadixThreads; ++r) {
 #pragma unroll
     for (int w = 0; w < 8; ++w) s_cnt[w][threadIdx.x] = 0;
@@ -501,7 +520,7 @@ __global__ void lov_finalize_kernel(const LovCtl* __restrict__ ctl, int n_heads,
 }
 
 struct LovLayout {
-  size_t ctl, valid, keys_a, keys_b, hist, tiles, total;
+  size_t ctl, valid, keys_a, keys_b, hist, tiles, dtot, total;
   int nblk_max;
 };
 
@@ -522,6 +541,7 @@ static LovLayout lov_layout(long long n_pix, int c, int n_heads) {
   L.keys_b = take((size_t)n_max * 8);
   L.hist = take((size_t)256 * L.nblk_max * 4);
   L.tiles = take((size_t)L.nblk_max * 4);
+  L.dtot = take(256 * 4);
   L.total = o;
   return L;
 }
@@ -580,6 +600,7 @@ extern "C" int pmfb_lovasz(const float* probs0, const float* probs1, const int64
   unsigned long long* kb = reinterpret_cast<unsigned long long*>(ws + L.keys_b);
   unsigned int* hist = reinterpret_cast<unsigned int*>(ws + L.hist);
   unsigned int* tiles = reinterpret_cast<unsigned int*>(ws + L.tiles);
+  unsigned int* dtot = reinterpret_cast<unsigned int*>(ws + L.dtot);
   const int per_pixel = c * n_heads;
   const long long* lab = reinterpret_cast<const long long*>(label);
 
@@ -597,9 +618,9 @@ extern "C" int pmfb_lovasz(const float* probs0, const float* probs1, const int64
     const int shift = kErrShift + 8 * pass;
     radix_hist_kernel<<<L.nblk_max, kRadixThreads, 0, st>>>(src, ctl, per_pixel, shift, hist, L.nblk_max);
     PMFB_LAUNCH_CHECK("radix_hist_kernel");
-    radix_scan_kernel<<<1, 1024, 0, st>>>(hist, ctl, per_pixel, L.nblk_max);
+    radix_scan_kernel<<<256, 1024, 0, st>>>(hist, ctl, per_pixel, L.nblk_max, dtot);
     PMFB_LAUNCH_CHECK("radix_scan_kernel");
-    radix_scatter_kernel<<<L.nblk_max, kRadixThreads, 0, st>>>(src, dst, ctl, per_pixel, shift, hist, L.nblk_max);
+    radix_scatter_kernel<<<L.nblk_max, kRadixThreads, 0, st>>>(src, dst, ctl, per_pixel, shift, hist, L.nblk_max, dtot);
     PMFB_LAUNCH_CHECK("radix_scatter_kernel");
     unsigned long long* t = src;
     src = dst;

@@ -380,7 +380,8 @@ class Engine:
         self._wg_list = []       # recorded convs in forward order (backward: one arena, one memset, one unpack launch)
         self._wg_arena = None
         self._wg_off = {}
-        self._unpack_table = None
+        self._unpack_tables = None
+        self.segments = None
         self.tape = []
         self.dropout = dropout  # see mask_for
         self.d64 = _Scratch(torch.float64, 1 << 17, device, self.st, zero=True)
@@ -531,26 +532,69 @@ class Engine:
             self._wg_list.append(cp)
         return fused if bn_stats is not None else e
 
+    # ---- backward segments (graph mode): the reversed tape is cut into K contiguous pieces of roughly equal convolution
+    # work; each piece becomes its own CUDA graph and autograd node, so that DDP's bucketed all-reduce of a piece's
+    # parameter gradients (tasks/pmf/trainer.py:38-39) overlaps the backward of the next pieces.
+    def plan_segments(self, k):
+        """Returns [(closures in execution order, parameter names produced)] * <= k for the recorded tape."""
+        rev = list(reversed(self.tape))
+        cost = [2.0 * getattr(f, "px", 0) * f.cp.taps * f.cp.c_in_p * f.cp.c_out_p if getattr(f, "cp", None) is not None else 0.0
+                for f in rev]
+        total = sum(cost) or 1.0
+        segs, cur, acc, done = [], [], 0.0, 0.0
+        for f, c in zip(rev, cost):
+            cur.append(f)
+            acc += c
+            if len(segs) < k - 1 and done + acc >= total * (len(segs) + 1) / k:
+                segs.append(cur)
+                done += acc
+                cur, acc = [], 0.0
+        if cur:
+            segs.append(cur)
+        out = []
+        for fs in segs:
+            names = []
+            for f in fs:
+                cp, bn = getattr(f, "cp", None), getattr(f, "bn", None)
+                if cp is not None:
+                    names.append(cp.name + ".weight")
+                    if cp.bias is not None:
+                        names.append(cp.name + ".bias")
+                if bn is not None:
+                    names += [bn.name + ".weight", bn.name + ".bias"]
+            out.append((fs, names))
+        self.segments = out
+        return out
+
     def prepare_backward(self):
         """Graph mode, called once BEFORE the backward capture: one arena for every packed weight gradient (zeroed by a
-        single memset per pass) and the device job table that unpacks all of them into the flat gradient buffer."""
+        single memset per pass) and, per backward segment, the device job table that unpacks that segment's weight
+        gradients into the flat gradient buffer."""
         if self.flat_views is None or not self._wg_list:
             return
-        jobs, off, start = [], 0, 0
+        if getattr(self, "segments", None) is None:
+            self.plan_segments(1)
         total = sum(cp.taps * cp.c_in_p * cp.c_out_p for cp in self._wg_list)
         self._wg_arena = torch.empty(total, device=self.device, dtype=torch.float32)
-        for cp in self._wg_list:
-            size = cp.taps * cp.c_in_p * cp.c_out_p
-            self._wg_off[cp.name] = (off, size)
-            gw = self.flat_views[cp.name + ".weight"]
-            j = WeightJob()
-            j.src, j.dst, j.dst2 = self._wg_arena.data_ptr() + 4 * off, gw.data_ptr(), None
-            j.c_out, j.c_in, j.kh, j.kw, j.stem = cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0
-            j.c_out_p, j.c_in_p, j.accumulate, j.start = cp.c_out_p, cp.c_in_p, 0, start
-            jobs.append(j)
-            off += size
-            start += cp.c_out * cp.c_in * cp.kh * cp.kw
-        self._unpack_table = (_job_table(jobs, self.device), len(jobs), start)
+        off = 0
+        self._unpack_tables = []
+        for fs, _names in self.segments:
+            jobs, start = [], 0
+            for f in fs:
+                cp = getattr(f, "cp", None)
+                if cp is None:
+                    continue
+                size = cp.taps * cp.c_in_p * cp.c_out_p
+                self._wg_off[cp.name] = (off, size)
+                gw = self.flat_views[cp.name + ".weight"]
+                j = WeightJob()
+                j.src, j.dst, j.dst2 = self._wg_arena.data_ptr() + 4 * off, gw.data_ptr(), None
+                j.c_out, j.c_in, j.kh, j.kw, j.stem = cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0
+                j.c_out_p, j.c_in_p, j.accumulate, j.start = cp.c_out_p, cp.c_in_p, 0, start
+                jobs.append(j)
+                off += size
+                start += cp.c_out * cp.c_in * cp.kh * cp.kw
+            self._unpack_tables.append((_job_table(jobs, self.device), len(jobs), start) if jobs else None)
 
     def _conv_bwd(self, x, cp, d_pre):
         """wgrad (+ dgrad into x's gradient) of out = conv(x) given d_pre = dL/d(conv output), tf32-rounded."""
@@ -732,6 +776,8 @@ class Engine:
                     self._bias_grad(cp, cs)
                 self._conv_bwd(x, cp, d_pre)
 
+            bwd.cp, bwd.bn = cp, None
+            bwd.px = y.shape[0] * y.shape[1] * y.shape[2]
             self.tape.append(bwd)
         return y
 
@@ -761,6 +807,8 @@ class Engine:
                     self._bias_grad(cp, cs)
                 self._conv_bwd(x, cp, d_pre)
 
+            bwd.cp, bwd.bn = cp, bn
+            bwd.px = shp[0] * shp[1] * shp[2]
             self.tape.append(bwd)
         return y
 
@@ -808,6 +856,8 @@ class Engine:
                     self._bias_grad(cp, cs)
                 self._conv_bwd(x, cp, d_pre)
 
+            bwd.cp, bwd.bn = cp, bn
+            bwd.px = shp[0] * shp[1] * shp[2]
             self.tape.append(bwd)
         return y
 
@@ -1003,16 +1053,36 @@ class Engine:
         self._side_keep = []
 
     def run_backward(self):
+        self.begin_backward()
+        for fn in reversed(self.tape):
+            fn()
+        self.join_side()
+        for tab in (self._unpack_tables or []):
+            if tab is not None:
+                L.call("pmfb_weight_jobs", 1, tab[0].data_ptr(), tab[1], tab[2], self.st)
+        self.tape = []
+        return self.param_grads
+
+    def begin_backward(self):
         self.st = torch.cuda.current_stream(self.device).cuda_stream
         self.d64 = _Scratch(torch.float64, 1 << 17, self.device, self.st, zero=True)
         self.f32.stream = self.st
         if self._wg_arena is not None:
             L.call("pmfb_memset_zero", self._wg_arena.data_ptr(), self._wg_arena.numel() * 4, self.st)
-        for fn in reversed(self.tape):
+
+    def run_backward_segment(self, k):
+        """Segment k of plan_segments (k = 0 runs first): its closures, the join of its side-stream wgrads and the unpack
+        of its weight gradients.  Segment 0 also does the per-pass set-up."""
+        self.st = torch.cuda.current_stream(self.device).cuda_stream
+        if k == 0:
+            self.begin_backward()
+        else:
+            self.d64.stream = self.st
+            self.f32.stream = self.st
+        for fn in self.segments[k][0]:
             fn()
         self.join_side()
-        if self._unpack_table is not None:
-            tab, n, total = self._unpack_table
-            L.call("pmfb_weight_jobs", 1, tab.data_ptr(), n, total, self.st)
-        self.tape = []
+        tab = self._unpack_tables[k] if self._unpack_tables else None
+        if tab is not None:
+            L.call("pmfb_weight_jobs", 1, tab[0].data_ptr(), tab[1], tab[2], self.st)
         return self.param_grads

@@ -321,17 +321,31 @@ class _GraphedPMF:
                                                                              mod.nclasses)
         self.n_fwd_calls = _L.launches - l0  # C-ABI launches one replay of the forward graph stands for
         _L.launches = l0                     # capturing enqueues nothing
-        self.n_bwd_calls = 0
         self.E = E
         self.ll_grad = self.cl_grad = None
-        # all parameter gradients live in ONE flat buffer: a single clone per step hands them to autograd
-        offs, total = {}, 0
-        for nm, p in mod.named_parameters():
-            offs[nm] = (total, p.numel(), tuple(p.shape))
-            total += (p.numel() + 3) // 4 * 4
-        self.flat = torch.zeros(total, device=self.dev, dtype=torch.float32)
-        self.offs = offs
-        E.flat_views = {nm: self.flat[o:o + k].view(shp) for nm, (o, k, shp) in offs.items()}
+        # ---- backward segments: K graphs / autograd nodes (DDP's bucketed all-reduce of segment k overlaps segment k+1)
+        self.segs = []
+        if record:
+            k = max(1, int(os.environ.get("PMFB_BWD_SEGMENTS", "4")))
+            plan = E.plan_segments(k)
+            produced = set(nm for _fs, names in plan for nm in names)
+            params = dict(mod.named_parameters())
+            # all parameter gradients live in ONE flat buffer laid out segment by segment: one clone per segment hands
+            # them to autograd
+            offs, total = {}, 0
+            for si, (_fs, names) in enumerate(plan):
+                start = total
+                seg_names = [nm for nm in names if nm in params]
+                for nm in seg_names:
+                    p = params[nm]
+                    offs[nm] = (total, p.numel(), tuple(p.shape))
+                    total += (p.numel() + 3) // 4 * 4
+                self.segs.append(dict(names=seg_names, lo=start, hi=total, graph=torch.cuda.CUDAGraph(), captured=False, calls=0))
+            self.unused = [nm for nm in params if nm not in produced]
+            self.flat = torch.zeros(max(total, 4), device=self.dev, dtype=torch.float32)
+            self.offs = offs
+            E.flat_views = {nm: self.flat[o:o + n_].view(shp) for nm, (o, n_, shp) in offs.items()}
+            self.prepared = False
 
     def _stage_inputs(self, pcd, img):
         self.E_in.st = torch.cuda.current_stream(self.dev).cuda_stream
@@ -345,35 +359,42 @@ class _GraphedPMF:
         self.version += 1
         return self.lidar.clone(), self.camera.clone()
 
-    def backward(self, d_lidar, d_camera):
+    def backward_segment(self, k, d_lidar=None, d_camera=None):
+        """Replays (capturing it the first time) backward segment k; returns {parameter name: gradient}."""
         E = self.E
-        st = torch.cuda.current_stream(self.dev).cuda_stream
-        if not self.bwd_captured:
-            self.ll_grad, _ = self.ll.grad_target()
-            self.cl_grad, _ = self.cl.grad_target()
-        E.softmax_backward_into(self.ll_grad, self.lidar, d_lidar, stream=st)
-        E.softmax_backward_into(self.cl_grad, self.camera, d_camera, stream=st)
-        if not self.bwd_captured:
-            E.prepare_backward()
+        seg = self.segs[k]
+        if k == 0:
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            if self.ll_grad is None:
+                self.ll_grad, _ = self.ll.grad_target()
+                self.cl_grad, _ = self.cl.grad_target()
+            E.softmax_backward_into(self.ll_grad, self.lidar, d_lidar, stream=st)
+            E.softmax_backward_into(self.cl_grad, self.camera, d_camera, stream=st)
+            if not self.prepared:
+                E.prepare_backward()
+                self.prepared = True
+        if not seg["captured"]:
             torch.cuda.synchronize(self.dev)
             l0 = _L.launches
-            with torch.cuda.graph(self.g_bwd, pool=self.pool, capture_error_mode="thread_local"):
-                self.grads = E.run_backward()
-            self.n_bwd_calls = _L.launches - l0
+            with torch.cuda.graph(seg["graph"], pool=self.pool, capture_error_mode="thread_local"):
+                E.run_backward_segment(k)
+            seg["calls"] = _L.launches - l0
             _L.launches = l0
-            self.bwd_captured = True
-        self.g_bwd.replay()
-        _L.launches += self.n_bwd_calls
-        out = self.flat.clone()
-        return tuple(out[o:o + k].view(shp) if nm in self.grads else None
-                     for nm, (o, k, shp) in ((nm, self.offs[nm]) for nm in self.names))
+            seg["captured"] = True
+        seg["graph"].replay()
+        _L.launches += seg["calls"]
+        out = self.flat[seg["lo"]:seg["hi"]].clone()
+        lo = seg["lo"]
+        return {nm: out[self.offs[nm][0] - lo:self.offs[nm][0] - lo + self.offs[nm][1]].view(self.offs[nm][2]) for nm in seg["names"]}
 
 
-class _PMFGraphFn(torch.autograd.Function):
+class _PMFGraphHeadFn(torch.autograd.Function):
+    """Last node of the forward chain = FIRST backward segment: owns the module outputs."""
+
     @staticmethod
-    def forward(ctx, runner, pcd, img, *params):
+    def forward(ctx, runner, pcd, img, token, *params):
         lidar, camera = runner.forward(pcd, img)
-        ctx.runner, ctx.version = runner, runner.version
+        ctx.runner, ctx.version, ctx.has_token = runner, runner.version, token is not None
         return lidar, camera
 
     @staticmethod
@@ -386,7 +407,39 @@ class _PMFGraphFn(torch.autograd.Function):
                                "CUDA-graph specialisation; set PMFB_CUDA_GRAPH=0 for call patterns other than "
                                "forward -> backward")
         with _on_device(d_lidar):
-            return (None, None, None) + r.backward(d_lidar, d_camera)
+            g = r.backward_segment(0, d_lidar, d_camera)
+            tok = torch.zeros(1, device=r.dev) if ctx.has_token else None
+        return (None, None, None, tok) + tuple(g[nm] for nm in r.segs[0]["names"])
+
+
+class _PMFGraphSegFn(torch.autograd.Function):
+    """Backward segment k >= 1.  In forward it only threads a token through, so that autograd runs the segments in
+    order; every node owns the parameters whose gradients its segment produces."""
+
+    @staticmethod
+    def forward(ctx, runner, k, token, *params):
+        ctx.runner, ctx.k, ctx.has_token = runner, k, token is not None
+        return torch.zeros(1, device=runner.dev)
+
+    @staticmethod
+    def backward(ctx, d_tok):
+        r = ctx.runner
+        with _on_device(d_tok):
+            g = r.backward_segment(ctx.k)
+            tok = torch.zeros(1, device=r.dev) if ctx.has_token else None
+        return (None, None, tok) + tuple(g[nm] for nm in r.segs[ctx.k]["names"])
+
+
+def _graph_apply(runner, pcd, img, named):
+    """Chains the segment nodes: the LAST backward segment is applied first.  Parameters no segment produces a gradient
+    for (none in PMFNet) ride on the head node and receive None."""
+    if not runner.record or len(runner.segs) <= 1:
+        names = runner.segs[0]["names"] if runner.segs else []
+        return _PMFGraphHeadFn.apply(runner, pcd, img, None, *[named[nm] for nm in names])
+    token = None
+    for k in range(len(runner.segs) - 1, 0, -1):
+        token = _PMFGraphSegFn.apply(runner, k, token, *[named[nm] for nm in runner.segs[k]["names"]])
+    return _PMFGraphHeadFn.apply(runner, pcd, img, token, *[named[nm] for nm in runner.segs[0]["names"]])
 
 
 class PMFNet(nn.Module):
@@ -457,7 +510,7 @@ class PMFNet(nn.Module):
                 runner = self._graphs[key] = _GraphedPMF(self, pcd_feature, img_feature, record)
             self._seen.add(key)
             if runner is not None:
-                return _PMFGraphFn.apply(runner, pcd_feature, img_feature, *params)
+                return _graph_apply(runner, pcd_feature, img_feature, dict(self.named_parameters()))
         return _PMFFn.apply(self, record, pcd_feature, img_feature, *params)
 
 
