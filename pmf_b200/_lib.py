@@ -124,6 +124,10 @@ def lib():
         if l.pmfb_abi_version() != ABI_VERSION:
             raise PmfbError("libpmf_b200.so ABI %d != binding ABI %d" % (l.pmfb_abi_version(), ABI_VERSION))
         _lib = l
+        trace = os.environ.get("PMFB_TRACE_LOADS")  # acceptance tests: prove which native library a process loaded
+        if trace:
+            with open(trace, "a") as f:
+                f.write("%d %s\n" % (os.getpid(), LIB_PATH))
     return _lib
 
 

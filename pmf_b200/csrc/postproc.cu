@@ -260,7 +260,9 @@ __global__ void merge_cameras_pass1(const long long* __restrict__ point_idx, con
     const long long j = point_idx[i];
     if (j < 0 || j >= pc_size) continue;
     const float c = conf[i];
-    if (!(c > 0.f)) continue;  // merge_conf starts at 0: a camera only wins with a positive confidence (argmax of zeros = cam 0 = -1)
+    // merge_conf starts at 0: a camera wins with a positive confidence; when every row is 0 torch.argmax picks row 0, i.e.
+    // camera 0's entry if it saw the point (even with confidence 0), else -1
+    if (!(c > 0.f) && !(c == 0.f && cam[i] == 0)) continue;
     const unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | ((unsigned long long)(7 - cam[i]) << 28) |
                                    (unsigned long long)(i & 0x0FFFFFFF);
     atomicMax(best + j, key);
@@ -271,7 +273,7 @@ __global__ void merge_cameras_pass2(const unsigned long long* __restrict__ best,
                                     long long pc_size, long long* __restrict__ merged) {
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < pc_size; j += (long long)gridDim.x * blockDim.x) {
     const unsigned long long key = best[j];
-    merged[j] = key != 0ull ? argmax[(long long)(key & 0x0FFFFFFFull)] : -1;  // low 28 bits: the winning entry
+    merged[j] = key != 0ull ? argmax[(long long)(key & 0x0FFFFFFFull)] : -1;  // low 28 bits: the winning entry (cam bits make key != 0)
   }
 }
 

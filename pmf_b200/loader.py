@@ -110,7 +110,9 @@ class PerspectiveViewLoader(Dataset):
         labels = torch.from_numpy(np.ascontiguousarray(self.dataset.labelMapping(sem_label), dtype=np.int32)).to(
             dev, non_blocking=True)
         proj = project_scatter(points, labels, self.dataset.proj_matrix[seq_id], h, w)
-        image_tensor = torch.from_numpy(image).to(dev, non_blocking=True).float().div_(255.0).permute(2, 0, 1)
+        # uint8 -> [0,1] exactly as perspective_view_loader.py:95 (a true fp32 division; torch's CUDA scalar division
+        # multiplies by the reciprocal, which differs in the last bit)
+        image_tensor = torch.from_numpy(image.astype(np.float32) / 255.0).to(dev, non_blocking=True).permute(2, 0, 1)
         proj_tensor = torch.cat((proj["feat"], image_tensor, proj["mask"].unsqueeze(0), proj["label"].unsqueeze(0)), dim=0)
 
         if self.return_uproj:
