@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
+    ap.add_argument("--ddp", default="flat", choices=["flat", "torch"],
+                    help="N > 1: pmf_b200.dist.FrameParallel (per-segment all-reduce of the flat gradient buffer) or stock torch DDP")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--kernel-timing", type=int, default=1, help="extra instrumented step for the roofline object")
@@ -259,7 +261,7 @@ def workload_config(B, H, W, world):
     return {"workload": "PMF-ResNet34 SemanticKITTI-shaped synthetic, batch %d/GPU, %dx%d camera grid, fwd + trainer loss block "
                         "(focal + Lovasz on both heads + perception-aware KL) + bwd + AdamW/SGD step, train-mode BN + Dropout2d"
                         % (B, H, W),
-            "frames_per_gpu": B, "height": H, "width": W, "parallelism": "ddp%d (frame-parallel)" % world,
+            "frames_per_gpu": B, "height": H, "width": W, "parallelism": "dp%d (frame-parallel, gradient all-reduce over NCCL)" % world,
             "l2": "no explicit flush: per-step working set (>20 GB of activations) >> 126 MB L2",
             "step_gflop_per_frame": STEP_KFLOP_PER_PX * px / 1e6}
 
@@ -380,9 +382,13 @@ def run_ours(args):
     model.train()
     net = model
     if world > 1:
-        # tasks/pmf/trainer.py:38-39, plus gradient_as_bucket_view: the 372 parameter gradients are reduced in place in
-        # DDP's buckets instead of being copied in and out by ~750 tiny kernels per step
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+        if args.ddp == "torch":
+            # tasks/pmf/trainer.py:38-39 (what the unchanged trainer builds), plus gradient_as_bucket_view
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+        else:
+            # pmf_b200.dist.FrameParallel: same semantics (rank-0 broadcast of parameters / BN buffers, averaged gradients),
+            # but the all-reduce runs per backward segment on the module's flat gradient buffer and overlaps the backward
+            net = pdist.wrap_ddp(model, local)
     opt_a, opt_b = make_optimizers(list(model.lidar_stream.parameters()),
                                    list(model.camera_stream_encoder.parameters()) + list(model.camera_stream_decoder.parameters()))
     # frame-parallel sharding: every rank owns its own B frames (weak scaling), no data-path collective
@@ -487,7 +493,7 @@ def run_ours(args):
         ms_ns = timed(step_nosync, k_ns) / k_ns
         ddp_info = {"ms_per_step_no_sync": ms_ns, "exposed_allreduce_ms": ms / args.steps - ms_ns,
                     "grad_bytes": sum(p.numel() for p in model.parameters()) * 4,
-                    "backward_segments": int(os.environ.get("PMFB_BWD_SEGMENTS", "4"))}
+                    "backward_segments": int(os.environ.get("PMFB_BWD_SEGMENTS", "4")), "wrapper": args.ddp}
 
     frames = B * world * args.steps
     value = frames / (ms * 1e-3)

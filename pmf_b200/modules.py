@@ -259,6 +259,7 @@ class _PMFFn(torch.autograd.Function):
     def forward(ctx, mod, record, pcd, img, *params):
         E = Engine(G.ModuleParams(mod), pcd.device, mod.training, record, mod._cache, dropout=mod._dropout_masks())
         lidar, camera, ll, cl = G.pmf_forward(E, pcd, img, mod.image_backbone, mod.nclasses)
+        ctx.mod = mod
         if record:
             ctx.E, ctx.ll, ctx.cl = E, ll, cl
             ctx.names = [n for n, _ in mod.named_parameters()]
@@ -278,6 +279,9 @@ class _PMFFn(torch.autograd.Function):
             E.softmax_backward(ctx.ll, lidar, d_lidar)
             E.softmax_backward(ctx.cl, camera, d_camera)
             grads = E.run_backward()
+            sync = getattr(ctx.mod, "_grad_sync", None)
+            if sync is not None and sync.enabled and sync.world() > 1:  # eager pass (first call of a specialisation)
+                sync.reduce_list([g for g in grads.values() if g is not None])
         ctx.E = None
         return (None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
@@ -385,7 +389,24 @@ class _GraphedPMF:
         _L.launches += seg["calls"]
         out = self.flat[seg["lo"]:seg["hi"]].clone()
         lo = seg["lo"]
-        return {nm: out[self.offs[nm][0] - lo:self.offs[nm][0] - lo + self.offs[nm][1]].view(self.offs[nm][2]) for nm in seg["names"]}
+        grads = {nm: out[self.offs[nm][0] - lo:self.offs[nm][0] - lo + self.offs[nm][1]].view(self.offs[nm][2]) for nm in seg["names"]}
+        sync = getattr(self.mod, "_grad_sync", None)
+        if sync is not None and sync.enabled and sync.world() > 1:
+            # pmf_b200.dist.FrameParallel: the segment's slice is averaged over the ranks asynchronously (it overlaps the
+            # next segments) and handed to the parameters directly, so autograd never reads it before the reduction is done
+            params = dict(self.mod.named_parameters())
+            plist = [params[nm] for nm in seg["names"] if params[nm].requires_grad]
+            sync.reduce(out, plist)
+            for nm in seg["names"]:
+                p = params[nm]
+                if not p.requires_grad:
+                    continue
+                if p.grad is None:
+                    p.grad = grads[nm]
+                else:
+                    p.grad.add_(grads[nm])
+            return {nm: None for nm in seg["names"]}
+        return grads
 
 
 class _PMFGraphHeadFn(torch.autograd.Function):

@@ -53,14 +53,14 @@ def _install_mock():
     return mpatch
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, flat=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     torch.set_num_threads(1)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     mpatch = _install_mock()
     try:
         m = _build()
-        ddp = pdist.wrap_ddp(m, rank)
+        ddp = pdist.wrap_ddp(m, rank, flat=flat)
         feat, label = _frames(rank)
         lid, cam = ddp(feat[:, 0:5], feat[:, 5:8])
         _loss(lid, cam, label).backward()
@@ -80,9 +80,12 @@ def test_shard_helpers():
 
 
 @pytest.mark.timeout(600)
-def test_ddp_two_ranks_gloo(tmp_path):
+@pytest.mark.parametrize("flat", [False, True], ids=["torch_ddp", "frame_parallel"])
+def test_ddp_two_ranks_gloo(tmp_path, flat):
+    """flat=False: stock DistributedDataParallel (what the unchanged trainer builds); flat=True: pmf_b200.dist.FrameParallel
+    (parameters / buffers broadcast from rank 0, gradients averaged by the module's own all-reduce)."""
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), flat), nprocs=2, join=True)
     g0 = torch.load(os.path.join(tmp_path, "grads_0.pt"))
     g1 = torch.load(os.path.join(tmp_path, "grads_1.pt"))
     # single-process reference: mean of the two ranks' gradients
