@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PMFB_ABI_VERSION 3
+#define PMFB_ABI_VERSION 4
 #define PMFB_MAX_TAPS 9
 
 typedef enum {
@@ -38,6 +38,13 @@ typedef enum {
   PMFB_ERR_CUDA = -2,      /* CUDA runtime / driver error        */
   PMFB_ERR_NO_DEVICE = -3  /* no sm_100 device available          */
 } pmfb_status;
+
+/* Operand storage of the implicit-GEMM kernels.  F32: fp32 values (pre-rounded to tf32), kind::tf32 UMMAs.  F16 / BF16:
+ * 16-bit "shadow" copies of the same NHWC views (see pmfb_convert16), kind::f16 UMMAs with fp32 accumulation: the same
+ * 32 bytes per operand row and instruction cover K = 16 channels instead of 8. */
+#define PMFB_DT_F32 0
+#define PMFB_DT_F16 1
+#define PMFB_DT_BF16 2
 
 typedef enum { PMFB_ACT_NONE = 0, PMFB_ACT_RELU = 1, PMFB_ACT_LEAKY = 2, PMFB_ACT_SIGMOID = 3 } pmfb_act;
 
@@ -94,6 +101,10 @@ typedef struct {
    * bn_stats[c_out:2*c_out] += sum of squares (double accumulators, caller zeroes; same contract as pmfb_bn_stats).
    * Only where pmfb_conv_fused_stats_ok(desc) returns 1; NULL = off. */
   double* bn_stats;
+  /* PMFB_DT_*: element type of x.ptr and w (x.strides stay in BYTES).  16-bit operands: stride-1 layers on the halo kernel
+   * only (pmfb_conv16_ok), c_in % 8 == 0. */
+  int32_t dtype;
+  int32_t reserved;
 } pmfb_conv_desc;
 
 /* Weight gradient on tcgen05: dw[tap][ci][co] += sum_{n,y,x} x[n,y+dh,x+dw,..,dc+ci] * dy[n,y,x,co]
@@ -121,6 +132,8 @@ int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream);
  * the halo kernel with a compile-time epilogue variant), else 0 (the caller then runs pmfb_bn_stats on the output). */
 int pmfb_conv_fused_stats_ok(const pmfb_conv_desc* d);
 int pmfb_conv_wgrad(const pmfb_wgrad_desc* d, void* stream);
+/* 1 if pmfb_conv_fwd accepts 16-bit operands (dtype F16 / BF16) for this geometry, else 0. */
+int pmfb_conv16_ok(const pmfb_conv_desc* d);
 
 /* ---------------------------------------------------------------------------------------------
  * Layout / packing kernels
@@ -177,6 +190,16 @@ int pmfb_unpack_wgrad(const float* packed, int32_t c_out, int32_t c_in, int32_t 
 int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n, int32_t h,
                    int32_t w, int32_t c, const pmfb_epilogue* epi, void* stream);
 
+/* pmfb_pointwise that ALSO stores the result as a 16-bit shadow (out16: same element strides and channel offset as out;
+ * dtype16 = PMFB_DT_F16 or PMFB_DT_BF16; values saturate to the fp16 range): the BN-apply pass that produces a conv input
+ * writes the operand the kind::f16 convolution will read in the same pass.  out16 == NULL: identical to pmfb_pointwise. */
+int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n, int32_t h,
+                     int32_t w, int32_t c, const pmfb_epilogue* epi, void* out16, int32_t dtype16, void* stream);
+
+/* 16-bit shadow of an fp32 NHWC view (c % 8 == 0; out16 has element strides o_sn / o_sy / o_sx, channel stride 1). */
+int pmfb_convert16(const pmfb_view* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out16, int64_t o_sn, int64_t o_sy,
+                   int64_t o_sx, int32_t dtype16, void* stream);
+
 /* sums[0:C] += sum_x, sums[C:2C] += sum_x^2 over all pixels (double accumulators, caller zeroes). */
 int pmfb_bn_stats(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, double* sums, void* stream);
 
@@ -211,6 +234,14 @@ int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view
                       int32_t h, int32_t w, int32_t c, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
                       int32_t round_out, float* dgamma, float* dbeta, double* colsum, float* g_out, int64_t g_sn,
                       int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* stream);
+
+/* pmfb_bn_bwd_apply that also stores dx as bf16 (dx16: same strides as dx): the operand of the kind::f16 dgrad. */
+int pmfb_bn_bwd_apply16(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z,
+                        const pmfb_view* x, const float* mean, const float* invstd, const float* alpha,
+                        const float* beta, const float* gamma, const double* red, int32_t leaky_x, int32_t n,
+                        int32_t h, int32_t w, int32_t c, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
+                        int32_t round_out, float* dgamma, float* dbeta, double* colsum, float* g_out, int64_t g_sn,
+                        int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* dx16, void* stream);
 
 /* out[i*C + c] (+)= sum over pixels (per image if per_image) of x; double accumulators, caller zeroes. */
 int pmfb_colsum(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t per_image, double* out,

@@ -8,10 +8,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmf_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_TAPS = 9
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
+DT_F32, DT_F16, DT_BF16 = 0, 1, 2
 
 f32p = C.c_void_p  # raw device pointers are passed as integers
 i32, i64 = C.c_int32, C.c_int64
@@ -36,7 +37,7 @@ class ConvDesc(C.Structure):
                 ("tap_dh", i32 * MAX_TAPS), ("tap_wi", i32 * MAX_TAPS), ("use_tap_wi", i32), ("n_batch", i32),
                 ("out_h", i32), ("out_w", i32), ("tile_w", i32),
                 ("tile_h", i32), ("n_tile", i32), ("out", C.c_void_p), ("o_sn", i64), ("o_sy", i64), ("o_sx", i64),
-                ("epi", Epilogue), ("bn_stats", C.c_void_p)]
+                ("epi", Epilogue), ("bn_stats", C.c_void_p), ("dtype", i32), ("reserved", i32)]
 
 
 class WgradDesc(C.Structure):
@@ -62,6 +63,11 @@ _SIGNATURES = {
     "pmfb_conv_fwd": ([C.POINTER(ConvDesc), vp], C.c_int),
     "pmfb_conv_fused_stats_ok": ([C.POINTER(ConvDesc)], C.c_int),
     "pmfb_conv_wgrad": ([C.POINTER(WgradDesc), vp], C.c_int),
+    "pmfb_conv16_ok": ([C.POINTER(ConvDesc)], C.c_int),
+    "pmfb_pointwise16": ([VP, vp, i64, i64, i64, i32, i32, i32, i32, C.POINTER(Epilogue), vp, i32, vp], C.c_int),
+    "pmfb_convert16": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
+    "pmfb_bn_bwd_apply16": ([VP, VP, VP, i32, VP, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i64, i64, i64,
+                             i32, vp, vp, vp, vp, i64, i64, i64, i32, vp, vp], C.c_int),
     "pmfb_memset_zero": ([vp, C.c_size_t, vp], C.c_int),
     "pmfb_pack_input": ([vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, vp, i32, i64, i32, vp], C.c_int),
     "pmfb_nhwc_to_nchw": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
@@ -159,7 +165,11 @@ def query(name, *args):
 #              class of the reference's own GPU path (cuDNN with allow_tf32)
 #   "3xtf32" : hi/lo operand split, three UMMAs per K step into the same TMEM accumulator (pmfb_split_tf32): fp32-class
 #              results, ~3x the tensor time; the parity mode for train-mode (batch-statistics) BatchNorm
-PRECISIONS = ("tf32", "3xtf32")
+#   "f16"    : the stride-1 convolutions read 16-bit shadows of their operands (fp16 activations and weights in the forward
+#              pass — the same 10-bit mantissa as tf32 — and bf16 output gradients / weights in dgrad), kind::f16 UMMAs with
+#              fp32 accumulation: K = 16 channels per instruction instead of 8 at the same operand bytes; everything else
+#              (BatchNorm, elementwise, wgrad, storage) stays fp32
+PRECISIONS = ("tf32", "3xtf32", "f16")
 _precision = os.environ.get("PMFB_PRECISION", "tf32").lower()
 if _precision not in PRECISIONS:
     raise PmfbError("PMFB_PRECISION must be one of %s, got %r" % (PRECISIONS, _precision))

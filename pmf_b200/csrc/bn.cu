@@ -9,6 +9,8 @@
 // lanes through shared memory and issues one fp64 atomicAdd per channel per CTA.
 #include <stdlib.h>
 
+#include <cuda_bf16.h>
+
 #include "common.h"
 #include "epilogue.cuh"
 
@@ -242,6 +244,7 @@ struct BnBwdApplyF {
   int C, leaky_x, round_out;
   PV dx;
   PV g_out;
+  unsigned short* dx16;  // optional bf16 copy of dx (same element offsets): the operand of the kind::f16 dgrad
   struct Loaded { typename GradIn<MUL, ZST>::Loaded i; float4 e[GACC ? 1 : 0]; };
   struct Consts { typename GradIn<MUL, ZST>::Consts i; float4 gi, m1, m2; };
   __device__ __forceinline__ void prep(int c, Consts& k) const {
@@ -284,7 +287,17 @@ struct BnBwdApplyF {
     if (round_out) {
       d.x = round_tf32(d.x); d.y = round_tf32(d.y); d.z = round_tf32(d.z); d.w = round_tf32(d.w);
     }
-    if (dx.p) *reinterpret_cast<float4*>(const_cast<float*>(pv_at(dx, pix, hw, w, c))) = d;
+    if (dx.p) {
+      float* dp = const_cast<float*>(pv_at(dx, pix, hw, w, c));
+      *reinterpret_cast<float4*>(dp) = d;
+      if (dx16) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(d.x, d.y), b = __floats2bfloat162_rn(d.z, d.w);
+        uint2 r;
+        r.x = *reinterpret_cast<const unsigned int*>(&a);
+        r.y = *reinterpret_cast<const unsigned int*>(&b);
+        *reinterpret_cast<uint2*>(dx16 + (dp - dx.p)) = r;
+      }
+    }
   }
 };
 
@@ -462,6 +475,7 @@ struct ApplyArgs {
   float* g_out;
   long long g_sn, g_sy, g_sx;
   void* stream;
+  void* dx16;
 };
 
 template <bool MUL, bool ZST, bool GACC>
@@ -479,6 +493,7 @@ static int bn_bwd_apply_t(const ApplyArgs& A) {
   f.leaky_x = A.leaky_x;
   f.round_out = A.round_out;
   f.dx = pv_out(A.dx, A.d_sn, A.d_sy, A.d_sx, A.h, A.w);
+  f.dx16 = static_cast<unsigned short*>(A.dx16);
   f.g_out = pv_out(A.g_out, A.g_sn, A.g_sy, A.g_sx, A.h, A.w);
   RedGrid g = red_grid(chan_reduce_kernel<1, F>, npix, A.c / 4, 1);
   chan_reduce_kernel<1, F><<<g.grid, kRedThreads, 0, (cudaStream_t)A.stream>>>(f, (unsigned)npix, (unsigned)(A.h * A.w), (unsigned)A.w,
@@ -509,6 +524,17 @@ extern "C" int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, cons
                                  int32_t h, int32_t w, int32_t c, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
                                  int32_t round_out, float* dgamma, float* dbeta, double* colsum, float* g_out, int64_t g_sn,
                                  int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* stream) {
+  return pmfb_bn_bwd_apply16(dy, mul, z, act_z, x, mean, invstd, alpha, beta, gamma, red, leaky_x, n, h, w, c, dx, d_sn, d_sy, d_sx,
+                             round_out, dgamma, dbeta, colsum, g_out, g_sn, g_sy, g_sx, g_accumulate, nullptr, stream);
+}
+
+extern "C" int pmfb_bn_bwd_apply16(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z,
+                                   const pmfb_view* x, const float* mean, const float* invstd, const float* alpha,
+                                   const float* beta, const float* gamma, const double* red, int32_t leaky_x, int32_t n,
+                                   int32_t h, int32_t w, int32_t c, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
+                                   int32_t round_out, float* dgamma, float* dbeta, double* colsum, float* g_out, int64_t g_sn,
+                                   int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* dx16, void* stream) {
+  REQ(!dx16 || (dx && (reinterpret_cast<uintptr_t>(dx16) & 7) == 0), "bn_bwd_apply16: dx16 needs dx and 8-byte alignment");
   REQ(c > 0 && c % 4 == 0, "bn_bwd_apply: c=%d", c);
   REQ(!mean || (gamma && red), "bn_bwd_apply: BN backward needs gamma and red");
   REQ(!leaky_x || (x && x->ptr), "bn_bwd_apply: leaky_x needs x");
@@ -516,7 +542,7 @@ extern "C" int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, cons
   REQ(!g_out || ((((g_sn | g_sy | g_sx) % 4) == 0) && ((reinterpret_cast<uintptr_t>(g_out) & 15) == 0)),
       "bn_bwd_apply: bad g_out view");
   ApplyArgs A{dy, mul, z, x, act_z, mean, invstd, alpha, beta, gamma, red, leaky_x, n, h, w, c, dx, d_sn, d_sy, d_sx, round_out,
-              dgamma, dbeta, colsum, g_out, g_sn, g_sy, g_sx, stream};
+              dgamma, dbeta, colsum, g_out, g_sn, g_sy, g_sx, stream, dx16};
   const int key = ((mul && mul->ptr) ? 4 : 0) | ((act_z && z && z->ptr) ? 2 : 0) | ((g_out && g_accumulate) ? 1 : 0);
   switch (key) {
     case 0: return bn_bwd_apply_t<false, false, false>(A);

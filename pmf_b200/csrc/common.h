@@ -25,6 +25,9 @@ encode_tiled_fn get_encode_tiled();
 //                        MN-major tf32 operands, i.e. the wgrad kernel).
 int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box, bool swizzle32b_atom = false);
+// 16-bit (fp16 / bf16) tensor map, 128B swizzle, zero OOB fill: the K-major UMMA operands of the kind::f16 path.
+int make_tmap_16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, bool bf16);
 
 #define PMFB_CUDA_CHECK(expr)                                                            \
   do {                                                                                   \

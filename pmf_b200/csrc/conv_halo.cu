@@ -41,6 +41,8 @@ struct HaloK {
   int tiles_x, tiles_y, n_batch, n_blocks;
   int out_h, out_w, c_out, n_tile;
   int nsb, a_bytes, a_box_bytes, nacc, tmem_cols, use_base_off, tma_store;
+  int dtype, kslab;  // operand type (PMFB_DT_*) and channels per 128-byte slab (32 fp32 / 64 16-bit)
+  int klast;         // 32-byte K steps of the LAST slab (a 32-channel layer fills half a 16-bit slab: 2 steps, not 4)
   float* out;
   long long o_sn, o_sy, o_sx;
   EpiParams epi;
@@ -141,13 +143,13 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
           const uint32_t ab = a_it & 1u;
           mbar_wait(&ctrl->empty_a[ab], ((a_it >> 1) & 1u) ^ 1u);
           mbar_expect_tx(&ctrl->full_a[ab], (uint32_t)P.a_box_bytes);
-          tma_load_5d(a_buf + (size_t)ab * P.a_bytes, &tmx, &ctrl->full_a[ab], s * 32, x0 - P.hx, 0, y0 - P.hy, n_img);
+          tma_load_5d(a_buf + (size_t)ab * P.a_bytes, &tmx, &ctrl->full_a[ab], s * P.kslab, x0 - P.hx, 0, y0 - P.hy, n_img);
           ++a_it;
           for (int t = 0; t < P.n_taps; ++t) {
             const uint32_t st = b_it % (uint32_t)P.nsb;
             mbar_wait(&ctrl->empty_b[st], ((b_it / (uint32_t)P.nsb) & 1u) ^ 1u);
             mbar_expect_tx(&ctrl->full_b[st], (uint32_t)b_bytes);
-            tma_load_3d(b_buf + (size_t)st * b_bytes, &tmw, &ctrl->full_b[st], s * 32, n0, P.tap_wi[t]);
+            tma_load_3d(b_buf + (size_t)st * b_bytes, &tmw, &ctrl->full_b[st], s * P.kslab, n0, P.tap_wi[t]);
             ++b_it;
           }
         }
@@ -159,7 +161,9 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
     // UTCHMMA made instruction issue, not the tensor pipe, the limiter); only the tcgen05 instructions are predicated
     // on one lane.  Descriptors are (constant high word | low word), and the low word advances by plain adds:
     // +2 (32 B >> 4) per K step, +(tap row/column offset) per tap, +(16 rows) per stacked tile.
-    const uint32_t idesc = make_idesc_tf32(128, (uint32_t)P.n_tile, 0, 0);
+    const bool f16 = P.dtype != PMFB_DT_F32;
+    const uint32_t idesc = f16 ? make_idesc_f16(128, (uint32_t)P.n_tile, P.dtype == PMFB_DT_BF16 ? 1u : 0u, 0, 0)
+                               : make_idesc_tf32(128, (uint32_t)P.n_tile, 0, 0);
     const uint32_t sbo = (uint32_t)pitch * 128u;
     const uint32_t hi_a = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // bits 32..63 of the A descriptor
     const uint32_t hi_b = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
@@ -184,12 +188,16 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
           const uint32_t b_lo = ((smem_u32(b_buf + (size_t)st * b_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
           uint32_t a_lo = a_lo0 + (uint32_t)((((P.tap_dh[t] + P.hy) * pitch + P.tap_dw[t] + P.hx) * 128) >> 4);
           uint32_t d_col = d_base;
+          const int kn = (s == P.ks - 1) ? P.klast : 4;
           for (int j = 0; j < P.mt; ++j) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = (static_cast<uint64_t>(hi_a) << 32) | (a_lo + 2u * k);
-              const uint64_t bd = (static_cast<uint64_t>(hi_b) << 32) | (b_lo + 2u * k);
-              umma_tf32_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
+              if (k < kn) {
+                const uint64_t ad = (static_cast<uint64_t>(hi_a) << 32) | (a_lo + 2u * k);
+                const uint64_t bd = (static_cast<uint64_t>(hi_b) << 32) | (b_lo + 2u * k);
+                if (f16) umma_f16_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
+                else umma_tf32_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
+              }
             }
             a_lo += j_step;
             d_col += (uint32_t)P.n_tile;
@@ -510,7 +518,15 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   }
   HaloK P;
   P.n_taps = d->n_taps;
-  P.ks = (d->c_in + 31) / 32;
+  P.dtype = d->dtype;
+  P.kslab = d->dtype == PMFB_DT_F32 ? 32 : 64;
+  if (d->dtype != PMFB_DT_F32 && d->c_in % 8) return fail(PMFB_ERR_INVALID, "conv halo: 16-bit operands need c_in %% 8 == 0 (c_in=%d)", d->c_in);
+  P.ks = (d->c_in + P.kslab - 1) / P.kslab;
+  {
+    const int per_step = P.kslab / 4;  // channels per 32-byte K step
+    const int rem = d->c_in - (P.ks - 1) * P.kslab;
+    P.klast = (rem + per_step - 1) / per_step;
+  }
   P.hx = P.hy = 0;
   for (int i = 0; i < PMFB_MAX_TAPS; ++i) {
     P.tap_dw[i] = d->tap_dw[i];
@@ -543,7 +559,7 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
     // own channel count clips them
     const int n_cands[3] = {n_full, (n_full % 64 == 0 && n_full >= 128) ? n_full / 2 : 0,
                             (n_full % 128 == 0 && n_full >= 256) ? n_full / 4 : 0};
-    const double ksteps = 4.0 * P.ks * d->n_taps;
+    const double ksteps = (4.0 * (P.ks - 1) + P.klast) * d->n_taps;
     for (int mi = 2; mi >= 1; --mi)
       for (int ni = 0; ni < 3; ++ni) {
         const int nt = n_cands[ni];
@@ -607,17 +623,20 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   if (rc) return rc;
 
   CUtensorMap tmx, tmw;
-  uint32_t boxx[5] = {32, (uint32_t)pitch, 1, (uint32_t)rows, 1};
-  rc = make_tmap_f32(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, boxx);
+  const bool h16 = d->dtype != PMFB_DT_F32;
+  const uint64_t esz = h16 ? 2 : 4;
+  uint32_t boxx[5] = {(uint32_t)P.kslab, (uint32_t)pitch, 1, (uint32_t)rows, 1};
+  rc = h16 ? make_tmap_16(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, boxx, d->dtype == PMFB_DT_BF16)
+           : make_tmap_f32(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, boxx);
   if (rc) return rc;
   int n_slabs = d->n_taps;
   if (d->use_tap_wi)
     for (int i = 0; i < d->n_taps; ++i)
       if (d->tap_wi[i] + 1 > n_slabs) n_slabs = d->tap_wi[i] + 1;
   uint64_t wdims[3] = {(uint64_t)d->c_in, (uint64_t)d->c_out, (uint64_t)n_slabs};
-  uint64_t wstr[2] = {(uint64_t)d->c_in * 4, (uint64_t)d->c_in * d->c_out * 4};
-  uint32_t boxw[3] = {32, (uint32_t)n_tile, 1};
-  rc = make_tmap_f32(&tmw, d->w, 3, wdims, wstr, boxw);
+  uint64_t wstr[2] = {(uint64_t)d->c_in * esz, (uint64_t)d->c_in * d->c_out * esz};
+  uint32_t boxw[3] = {(uint32_t)P.kslab, (uint32_t)n_tile, 1};
+  rc = h16 ? make_tmap_16(&tmw, d->w, 3, wdims, wstr, boxw, d->dtype == PMFB_DT_BF16) : make_tmap_f32(&tmw, d->w, 3, wdims, wstr, boxw);
   if (rc) return rc;
 
   CUtensorMap tmo = tmw;  // placeholder when the direct-store path is used

@@ -328,6 +328,13 @@ extern "C" int pmfb_conv_fused_stats_ok(const pmfb_conv_desc* d) {
   return (halo_eligible(d) && halo_fused_stats_ok(d)) ? 1 : 0;
 }
 
+extern "C" int pmfb_conv16_ok(const pmfb_conv_desc* d) {
+  if (!d || d->n_taps < 1 || d->n_taps > PMFB_MAX_TAPS || d->c_in % 8) return 0;
+  const char* e = getenv("PMFB_CONV_V1");
+  if (e && atoi(e)) return 0;
+  return halo_eligible(d) ? 1 : 0;
+}
+
 extern "C" int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream) {
   if (!d) return fail(PMFB_ERR_INVALID, "null desc");
   if (d->n_taps < 1 || d->n_taps > PMFB_MAX_TAPS) return fail(PMFB_ERR_INVALID, "n_taps=%d", d->n_taps);
@@ -344,6 +351,7 @@ extern "C" int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream) {
     }
     if (!force_v1 && halo_eligible(d)) return launch_conv_halo(d, stream);
   }
+  if (d->dtype != PMFB_DT_F32) return fail(PMFB_ERR_INVALID, "conv_fwd: 16-bit operands are only supported on the stride-1 halo kernel (query pmfb_conv16_ok)");
   if (d->bn_stats) return fail(PMFB_ERR_INVALID, "conv_fwd: fused BN statistics are not available for this layer (query pmfb_conv_fused_stats_ok)");
   if (d->tile_w * d->tile_h != kTileM) return fail(PMFB_ERR_INVALID, "tile_w*tile_h must be 128");
   if (d->n_tile < 16 || d->n_tile > 256 || d->n_tile % 16)

@@ -7,10 +7,31 @@
 //   pixel_shuffle    : nn.PixelShuffle(2) salsanext.py:137
 //   upsample2x       : nn.Upsample(scale_factor=2, mode="bilinear") pmf_net.py:191-210
 //   softmax_nchw     : F.softmax(dim=1) pmf_net.py:177-178,221
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.h"
 #include "epilogue.cuh"
 
 namespace pmfb {
+
+// four fp32 values -> four 16-bit values (8 bytes).  fp16 saturates to +-65504 (conv inputs are O(1..100); an overflow to
+// inf would poison a whole accumulator row).
+__device__ __forceinline__ uint2 pack16(float4 v, int dt) {
+  uint2 r;
+  if (dt == PMFB_DT_BF16) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    r.x = *reinterpret_cast<const unsigned int*>(&a);
+    r.y = *reinterpret_cast<const unsigned int*>(&b);
+  } else {
+    const float m = 65504.f;
+    const __half2 a = __floats2half2_rn(fminf(fmaxf(v.x, -m), m), fminf(fmaxf(v.y, -m), m));
+    const __half2 b = __floats2half2_rn(fminf(fmaxf(v.z, -m), m), fminf(fmaxf(v.w, -m), m));
+    r.x = *reinterpret_cast<const unsigned int*>(&a);
+    r.y = *reinterpret_cast<const unsigned int*>(&b);
+  }
+  return r;
+}
 
 static inline int grid_for(long long work, int threads, int max_blocks = 148 * 16) {
   long long b = (work + threads - 1) / threads;
@@ -51,6 +72,8 @@ struct PWParams {
   const float* alpha2;
   const float* beta2;
   int act, round_out;
+  unsigned short* out16;  // optional 16-bit shadow of the result (same element offsets as out)
+  int dt16;
 };
 
 // OPS (bit 0: r1, bit 1: mul, bit 2: r2) is a compile-time mask of the per-pixel operands: the common launches (BN apply,
@@ -93,7 +116,9 @@ pointwise_kernel(PWParams P, unsigned npix, unsigned hw, unsigned w, int c4, int
         if constexpr (kMul) { o.x *= mu[k].x; o.y *= mu[k].y; o.z *= mu[k].z; o.w *= mu[k].w; }
         if constexpr (kR2) { o.x += r2[k].x; o.y += r2[k].y; o.z += r2[k].z; o.w += r2[k].w; }
         if (P.round_out) o = rnd4(o);
-        *reinterpret_cast<float4*>(const_cast<float*>(pw_at(P.out, p, hw, w, c))) = o;
+        float* op = const_cast<float*>(pw_at(P.out, p, hw, w, c));
+        *reinterpret_cast<float4*>(op) = o;
+        if (P.out16) *reinterpret_cast<uint2*>(P.out16 + (op - P.out.p)) = pack16(o, P.dt16);
       }
     }
   }
@@ -648,7 +673,15 @@ static inline PWV pwv(const float* p, long long sn, long long sy, long long sx, 
 
 extern "C" int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n,
                               int32_t h, int32_t w, int32_t c, const pmfb_epilogue* epi, void* stream) {
+  return pmfb_pointwise16(in, out, o_sn, o_sy, o_sx, n, h, w, c, epi, nullptr, PMFB_DT_F16, stream);
+}
+
+extern "C" int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n,
+                                int32_t h, int32_t w, int32_t c, const pmfb_epilogue* epi, void* out16, int32_t dtype16,
+                                void* stream) {
   REQ(epi && c > 0 && c % 4 == 0, "pointwise: c=%d must be a positive multiple of 4", c);
+  REQ(!out16 || ((dtype16 == PMFB_DT_F16 || dtype16 == PMFB_DT_BF16) && (reinterpret_cast<uintptr_t>(out16) & 7) == 0),
+      "pointwise16: the 16-bit output must be 8-byte aligned, dtype F16 or BF16");
   REQ(out_ok(out, o_sn, o_sy, o_sx), "pointwise: bad output view");
   REQ(!in || view_ok(in), "pointwise: bad input view");
   EpiParams E;
@@ -669,6 +702,8 @@ extern "C" int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int
   P.beta2 = E.beta2;
   P.act = E.act;
   P.round_out = E.round_out;
+  P.out16 = static_cast<unsigned short*>(out16);
+  P.dt16 = dtype16;
   const int ops = (P.r1.p ? 1 : 0) | (P.mul.p ? 2 : 0) | (P.r2.p ? 4 : 0);
   const cudaStream_t st = (cudaStream_t)stream;
   switch (ops) {
@@ -727,6 +762,38 @@ extern "C" int pmfb_unpack_wgrad(const float* packed, int32_t c_out, int32_t c_i
   unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, c_out, c_in, kh, kw, stem, c_out_p, c_in_p,
                                                                               grad, accumulate);
   PMFB_LAUNCH_CHECK("unpack_wgrad_kernel");
+  return PMFB_OK;
+}
+
+// ------------------------------------------------------------------------------------ 16-bit shadows
+namespace pmfb {
+__global__ void __launch_bounds__(256)
+convert16_kernel(EpiView x, int n, int h, int w, int c4, unsigned short* __restrict__ out, long long o_sn, long long o_sy,
+                 long long o_sx, int dt) {
+  const long long total = (long long)n * h * w * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % c4);
+    long long r = i / c4;
+    const int xx = (int)(r % w);
+    r /= w;
+    const int yy = (int)(r % h);
+    const int nn = (int)(r / h);
+    const float4 v = ld4(x.p + (long long)nn * x.sn + (long long)yy * x.sy + (long long)xx * x.sx + 4 * q);
+    *reinterpret_cast<uint2*>(out + (long long)nn * o_sn + (long long)yy * o_sy + (long long)xx * o_sx + 4 * q) = pack16(v, dt);
+  }
+}
+}  // namespace pmfb
+
+extern "C" int pmfb_convert16(const pmfb_view* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out16, int64_t o_sn,
+                              int64_t o_sy, int64_t o_sx, int32_t dtype16, void* stream) {
+  REQ(in && in->ptr && out16 && c > 0 && c % 4 == 0, "convert16: bad arguments");
+  REQ(dtype16 == PMFB_DT_F16 || dtype16 == PMFB_DT_BF16, "convert16: dtype must be F16 or BF16");
+  REQ(view_ok(in) && ((o_sn | o_sy | o_sx) % 4) == 0 && (reinterpret_cast<uintptr_t>(out16) & 7) == 0, "convert16: bad views");
+  const long long total = (long long)n * h * w * (c / 4);
+  if (total == 0) return PMFB_OK;
+  convert16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(in), n, h, w, c / 4, static_cast<unsigned short*>(out16),
+                                                                          o_sn, o_sy, o_sx, dtype16);
+  PMFB_LAUNCH_CHECK("convert16_kernel");
   return PMFB_OK;
 }
 

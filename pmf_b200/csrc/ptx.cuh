@@ -151,6 +151,18 @@ __device__ __forceinline__ void umma_tf32_warp(uint32_t tmem_d, uint64_t adesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (fp16 or bf16 operands, fp32 accumulate): K = 16 per instruction, i.e. the same 32 bytes per operand row as a
+// kind::tf32 K = 8 step, so the descriptor arithmetic of the tf32 loops carries over unchanged.
+__device__ __forceinline__ void umma_f16_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
@@ -211,6 +223,20 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t M, uint32_
   d |= 1u << 4;
   d |= 2u << 7;
   d |= 2u << 10;
+  d |= (a_mn_major & 1u) << 15;
+  d |= (b_mn_major & 1u) << 16;
+  d |= ((N >> 3) & 0x3Fu) << 17;
+  d |= ((M >> 4) & 0x1Fu) << 24;
+  return d;
+}
+
+// Instruction descriptor for kind::f16 with fp32 accumulation: a_format / b_format 0 = F16, 1 = BF16.
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t bf16, uint32_t a_mn_major,
+                                                            uint32_t b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= (bf16 & 1u) << 7;
+  d |= (bf16 & 1u) << 10;
   d |= (a_mn_major & 1u) << 15;
   d |= (b_mn_major & 1u) << 16;
   d |= ((N >> 3) & 0x3Fu) << 17;

@@ -54,7 +54,7 @@ def _p(t):
 
 class Act:
     """An NHWC activation: ``t`` is a (N,H,W,C) torch view; slices share the root's gradient buffer."""
-    __slots__ = ("t", "root", "c0", "needs_grad", "_round_grad", "grad", "gcov")
+    __slots__ = ("t", "root", "c0", "needs_grad", "_round_grad", "grad", "gcov", "h", "hcov")
 
     def __init__(self, t, root=None, c0=0, needs_grad=True):
         self.t = t
@@ -64,6 +64,29 @@ class Act:
         self._round_grad = False  # root only; see round_grad
         self.grad = None         # root only: dense NHWC gradient buffer
         self.gcov = []           # root only: channel intervals of grad already written
+        self.h = None            # root only ("f16" mode): fp16 shadow of t, the operand of the kind::f16 convolutions
+        self.hcov = []           # root only: channel intervals of the shadow that hold current values
+
+    # ---- 16-bit shadow ("f16" precision mode)
+    def shadow(self):
+        """fp16 view matching self.t, or None when this buffer has no shadow."""
+        r = self.root
+        return None if r.h is None else r.h[..., self.c0:self.c0 + self.c]
+
+    def shadow_valid(self):
+        a, b = self.c0, self.c0 + self.c
+        return any(x <= a and b <= y for (x, y) in self.root.hcov)
+
+    def shadow_mark(self):
+        a, b = self.c0, self.c0 + self.c
+        iv = sorted(self.root.hcov + [(a, b)])
+        merged = [iv[0]]
+        for (x, y) in iv[1:]:
+            if x <= merged[-1][1]:
+                merged[-1] = (merged[-1][0], max(merged[-1][1], y))
+            else:
+                merged.append((x, y))
+        self.root.hcov = merged
 
     @property
     def shape(self):
@@ -219,6 +242,16 @@ class WeightCache:
         self.epoch = 0
         self.table = None
         self.precise = False  # set by the Engine of the pass (pmf_b200._lib precision mode)
+        self.h16 = False      # "f16" mode: fp16 forward / bf16 dgrad copies of the packed weights
+        self.arenas = None
+
+    @staticmethod
+    def _convert16(src, dst, dt, stream):
+        """flat fp32 packed weights -> 16-bit copy (pmfb_convert16 on a (1,1,size/16,16) view; sizes are multiples of 16)."""
+        n16 = src.numel() // 16
+        v = View()
+        v.ptr, v.sn, v.sy, v.sx = src.data_ptr(), 0, 0, 16
+        L.call("pmfb_convert16", C.byref(v), 1, 1, n16, 16, dst.data_ptr(), 0, 0, 16, dt, stream)
 
     def _split3(self, cp, e, stream):
         """Precise mode: [hi|lo|hi] split packings of the (un-rounded) packed weights (pmfb_split_tf32 mode 1)."""
@@ -247,11 +280,16 @@ class WeightCache:
             self.table = None
             return
         jobs, start = [], 0
+        total = sum(cp.taps * cp.c_out_p * cp.c_in_p for cp in convs)
+        A = {"fwd": torch.empty(total, device=device, dtype=torch.float32),
+             "dgrad": torch.empty(total, device=device, dtype=torch.float32) if need_dgrad else None,
+             "fwd16": torch.empty(total, device=device, dtype=torch.float16) if self.h16 else None,
+             "dgrad16": torch.empty(total, device=device, dtype=torch.bfloat16) if (self.h16 and need_dgrad) else None}
+        self.arenas = A
         for cp in convs:
             size = cp.taps * cp.c_out_p * cp.c_in_p
-            e = {"fwd": torch.empty(size, device=device, dtype=torch.float32),
-                 "dgrad": torch.empty(size, device=device, dtype=torch.float32) if need_dgrad else None,
-                 "bias": None, "tag": None}
+            e = {k: (None if A[k] is None else A[k][start:start + size]) for k in ("fwd", "dgrad", "fwd16", "dgrad16")}
+            e.update(bias=None, tag=None)
             self.entries[cp.name] = e
             j = WeightJob()
             j.src, j.dst, j.dst2 = cp.weight.data_ptr(), e["fwd"].data_ptr(), _p(e["dgrad"])
@@ -265,6 +303,10 @@ class WeightCache:
     def pack_all(self, stream):
         tab, n, total, convs, need_dgrad = self.table
         L.call("pmfb_weight_jobs", 0, tab.data_ptr(), n, total, stream)
+        if self.h16 and self.arenas is not None:  # ONE conversion launch per arena
+            self._convert16(self.arenas["fwd"], self.arenas["fwd16"], L.DT_F16, stream)
+            if self.arenas["dgrad16"] is not None:
+                self._convert16(self.arenas["dgrad"], self.arenas["dgrad16"], L.DT_BF16, stream)
         tag = ("epoch", self.epoch)
         for cp in convs:
             e = self.entries[cp.name]
@@ -290,7 +332,7 @@ class WeightCache:
         else:
             # re-packed once per pass (Engine): in-place updates through ``.data`` (EMA swaps, manual clipping) do not
             # bump ``_version``, so a version tag alone would keep convolving with stale packed weights
-            tag = (self.epoch, w.data_ptr(), None if cp.bias is None else cp.bias.data_ptr(), need_dgrad, self.precise)
+            tag = (self.epoch, w.data_ptr(), None if cp.bias is None else cp.bias.data_ptr(), need_dgrad, self.precise, self.h16)
             if e is not None and e["tag"] == tag:
                 return e
         dev = w.device
@@ -306,6 +348,12 @@ class WeightCache:
                cp.c_in_p, e["fwd"].data_ptr(), _p(e["dgrad"]) if need_dgrad else None, 0 if self.precise else 1, stream)
         if self.precise:
             self._split3(cp, e, stream)
+        if self.h16:
+            e["fwd16"] = torch.empty(e["fwd"].numel(), device=dev, dtype=torch.float16)
+            self._convert16(e["fwd"], e["fwd16"], L.DT_F16, stream)
+            if need_dgrad:
+                e["dgrad16"] = torch.empty(e["dgrad"].numel(), device=dev, dtype=torch.bfloat16)
+                self._convert16(e["dgrad"], e["dgrad16"], L.DT_BF16, stream)
         if cp.bias is not None:
             if cp.c_out_p != cp.c_out:
                 b = torch.zeros(cp.c_out_p, device=dev, dtype=torch.float32)
@@ -371,7 +419,11 @@ class Engine:
         # precision mode of the tensor-core convolutions (pmf_b200._lib): in "3xtf32" nothing is rounded where it is
         # produced (self.R = 0) and every conv operand is split into tf32 hi/lo parts right before the launch
         self.precise = L.get_precision() == "3xtf32"
+        # "f16": training passes feed the stride-1 convolutions from 16-bit shadows (fp16 forward operands, bf16 output
+        # gradients in dgrad); eval passes fuse everything into the conv epilogues and stay on the tf32 path
+        self.h16 = L.get_precision() == "f16" and self.train and str(device).startswith("cuda")
         self.R = 0 if self.precise else 1
+        self.cache.h16 = self.h16
         self.cache.precise = self.precise
         self.cache.begin_pass()
         self.st = torch.cuda.current_stream(device).cuda_stream
@@ -386,6 +438,7 @@ class Engine:
         self.dropout = dropout  # see mask_for
         self.d64 = _Scratch(torch.float64, 1 << 17, device, self.st, zero=True)
         self.f32 = _Scratch(torch.float32, 1 << 17, device, self.st, zero=False)
+        self._dpre16 = None
         self.param_grads = {}
         self.flat_views = None  # graph mode: {param name: view into one flat gradient buffer}
         self.nbt_list = []
@@ -404,7 +457,22 @@ class Engine:
         return torch.empty_like(like, memory_format=torch.contiguous_format)
 
     def new(self, n, h, w, c, needs_grad=True):
-        return Act(torch.empty((n, h, w, c), device=self.device, dtype=torch.float32), needs_grad=needs_grad)
+        a = Act(torch.empty((n, h, w, c), device=self.device, dtype=torch.float32), needs_grad=needs_grad)
+        if self.h16 and c % 8 == 0:
+            a.h = torch.empty((n, h, w, c), device=self.device, dtype=torch.float16)
+        return a
+
+    def _ensure_shadow(self, x):
+        """fp16 shadow view of Act x with current values (converted here if its producer did not write it), or None."""
+        sh = x.shadow()
+        if sh is None:
+            return None
+        if not x.shadow_valid():
+            n, h, w, c = x.shape
+            L.call("pmfb_convert16", C.byref(_view(x.t)), n, h, w, c, sh.data_ptr(), sh.stride(0), sh.stride(1), sh.stride(2),
+                   L.DT_F16, self.st)
+            x.shadow_mark()
+        return sh
 
     def _epi(self, alpha1=None, beta1=None, alpha2=None, beta2=None, r1=None, mul=None, r2=None, act=ACT_NONE, rnd=0):
         e = Epilogue()
@@ -416,11 +484,19 @@ class Engine:
         e.act, e.round_out = act, (rnd if self.R else 0)
         return e
 
-    def pointwise(self, src, dst, **kw):
-        """dst = epilogue(src) elementwise; src None means zeros; src may be a View (broadcast)."""
+    def pointwise(self, src, dst, shadow=None, **kw):
+        """dst = epilogue(src) elementwise; src None means zeros; src may be a View (broadcast).  ``shadow``: the Act that
+        owns ``dst``; in "f16" mode its fp16 shadow is written by the same pass."""
         n, h, w, c = dst.shape
         e = self._epi(**kw)
         sv = src if isinstance(src, View) else _view(src)
+        sh = shadow.shadow() if (self.h16 and shadow is not None) else None
+        if sh is not None:
+            assert tuple(sh.stride()) == tuple(dst.stride()), (sh.stride(), dst.stride())
+            L.call("pmfb_pointwise16", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
+                   C.byref(e), sh.data_ptr(), L.DT_F16, self.st)
+            shadow.shadow_mark()
+            return
         L.call("pmfb_pointwise", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
                C.byref(e), self.st)
 
@@ -465,14 +541,16 @@ class Engine:
         s = TmaSrc()
         n, h, w, _ = t.shape
         sn, sy, sx = t.stride(0), t.stride(1), t.stride(2)
+        es = t.element_size()
         s.ptr = t.data_ptr()
+        s._keep = t
         if not stride2:
             s.dims[:] = [c, w, 1, h, n]
-            s.strides[:] = [sx * 4, sy * 4, sy * 4, sn * 4]
+            s.strides[:] = [sx * es, sy * es, sy * es, sn * es]
         else:
             assert sx == c and h % 2 == 0 and w % 2 == 0, "stride-2 convs need a dense NHWC input"
             s.dims[:] = [2 * c, w // 2, 2, h // 2, n]
-            s.strides[:] = [2 * sx * 4, sy * 4, 2 * sy * 4, sn * 4]
+            s.strides[:] = [2 * sx * es, sy * es, 2 * sy * es, sn * es]
         return s
 
     def split(self, t, mode):
@@ -485,9 +563,12 @@ class Engine:
                mode, self.st)
         return out
 
-    def _conv_launch(self, x_t, c_in, stride2, w_packed, c_out, taps, n, out_h, out_w, out_t, epi, bn_stats=None):
+    def _conv_launch(self, x_t, c_in, stride2, w_packed, c_out, taps, n, out_h, out_w, out_t, epi, bn_stats=None, x16=None,
+                     w16=None, dt16=0):
         """Returns True when ``bn_stats`` (2*c_out fp64 sums, zeroed) was accumulated by the conv's own epilogue.
-        Precise mode: ``w_packed`` is the [hi|lo|hi] split packing over 3*roundup(c_in,32) channels and x is split here."""
+        Precise mode: ``w_packed`` is the [hi|lo|hi] split packing over 3*roundup(c_in,32) channels and x is split here.
+        "f16" mode: ``x16`` / ``w16`` are 16-bit shadows of x_t / w_packed (dt16 = DT_F16 or DT_BF16); they are used when the
+        library accepts 16-bit operands for this geometry (pmfb_conv16_ok), else the fp32 operands."""
         if self.precise:
             c3 = 3 * _rup(c_in, 32)
             x_t = self.split(x_t, 0)
@@ -508,6 +589,10 @@ class Engine:
         d.o_sn, d.o_sy, d.o_sx = out_t.stride(0), out_t.stride(1), out_t.stride(2)
         d.epi = epi
         d.bn_stats = None
+        if x16 is not None and w16 is not None and not stride2 and c_in % 8 == 0 and L.query("pmfb_conv16_ok", C.byref(d)) == 1:
+            d.x = self._tma_src(x16, c_in, False)
+            d.w = w16.data_ptr()
+            d.dtype = dt16
         fused = False
         if bn_stats is not None and L.query("pmfb_conv_fused_stats_ok", C.byref(d)) == 1:
             d.bn_stats = bn_stats.data_ptr()
@@ -526,8 +611,9 @@ class Engine:
             oh = (h + 2 * cp.pad - cp.dil * (cp.kh - 1) - 1) // cp.stride + 1
             ow = (w + 2 * cp.pad - cp.dil * (cp.kw - 1) - 1) // cp.stride + 1
         assert tuple(out_t.shape) == (n, oh, ow, cp.c_out_p), (cp.name, tuple(out_t.shape), (n, oh, ow, cp.c_out_p))
+        x16 = self._ensure_shadow(x) if (self.h16 and cp.stride == 1 and cp.c_in_p % 8 == 0 and e.get("fwd16") is not None) else None
         fused = self._conv_launch(x.t, cp.c_in_p, cp.stride == 2, e["fwd3" if self.precise else "fwd"], cp.c_out_p, cp.fwd_taps(),
-                                  n, oh, ow, out_t, epi, bn_stats=bn_stats)
+                                  n, oh, ow, out_t, epi, bn_stats=bn_stats, x16=x16, w16=e.get("fwd16"), dt16=L.DT_F16)
         if self.record:
             self._wg_list.append(cp)
         return fused if bn_stats is not None else e
@@ -598,6 +684,9 @@ class Engine:
 
     def _conv_bwd(self, x, cp, d_pre):
         """wgrad (+ dgrad into x's gradient) of out = conv(x) given d_pre = dL/d(conv output), tf32-rounded."""
+        d16, self._dpre16 = self._dpre16, None  # bf16 shadow of d_pre left by _bn_backward for THIS layer (or None)
+        if d16 is not None and tuple(d16.shape) != tuple(d_pre.shape):
+            d16 = None
         e = self.cache.get(cp, True, self.st)
         n, h, w, _ = x.shape
         _, oh, ow, co = d_pre.shape
@@ -659,7 +748,7 @@ class Engine:
         if cp.stride == 1:
             taps = [(0, -dw, 0, -dh, wi) for (_dc, dw, _dp, dh, wi) in cp.fwd_taps()]
             self._conv_launch(d_pre, cp.c_out_p, False, w_dgrad, cp.c_in_p, taps, n, h, w, gx,
-                              self._epi(r1=gx if acc else None, rnd=rnd))
+                              self._epi(r1=gx if acc else None, rnd=rnd), x16=d16, w16=e.get("dgrad16"), dt16=L.DT_BF16)
             return
         # stride 2: one stride-1 convolution over dy per input parity class
         for py in (0, 1):
@@ -676,7 +765,7 @@ class Engine:
                         self.pointwise(None, sub)
                     continue
                 self._conv_launch(d_pre, cp.c_out_p, False, w_dgrad, cp.c_in_p, taps, n, h // 2, w // 2, sub,
-                                  self._epi(r1=sub if acc else None, rnd=rnd))
+                                  self._epi(r1=sub if acc else None, rnd=rnd), x16=d16, w16=e.get("dgrad16"), dt16=L.DT_BF16)
 
     def _bias_grad(self, cp, colsum64):
         gb = self._pgrad(cp.name + ".bias", cp.bias)
@@ -727,11 +816,13 @@ class Engine:
         d_pre = torch.empty((n, h, w, c), device=self.device, dtype=torch.float32)
         cs = self.d64.take(c) if want_colsum else None
         gw, gb = self._pgrad(bn.name + ".weight", bn.weight), self._pgrad(bn.name + ".bias", bn.bias)
-        L.call("pmfb_bn_bwd_apply", C.byref(dyv), C.byref(mulv), C.byref(zv), act_z, C.byref(xv), mean.data_ptr(),
+        # "f16" mode: the same pass also stores d_pre as bf16, the operand of the kind::f16 dgrad
+        self._dpre16 = torch.empty((n, h, w, c), device=self.device, dtype=torch.bfloat16) if (self.h16 and c % 8 == 0) else None
+        L.call("pmfb_bn_bwd_apply16", C.byref(dyv), C.byref(mulv), C.byref(zv), act_z, C.byref(xv), mean.data_ptr(),
                invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), bn.weight.detach().data_ptr(), red.data_ptr(), leaky_x,
                n, h, w, c, d_pre.data_ptr(), d_pre.stride(0), d_pre.stride(1), d_pre.stride(2), self.R, gw.data_ptr(),
                gb.data_ptr(), _p(cs), _p(g_out), *( (g_out.stride(0), g_out.stride(1), g_out.stride(2)) if g_out is not None
-                                                    else (0, 0, 0)), 1 if g_acc else 0, self.st)
+                                                    else (0, 0, 0)), 1 if g_acc else 0, _p(self._dpre16), self.st)
         self.param_grads[bn.name + ".weight"] = gw
         self.param_grads[bn.name + ".bias"] = gb
         return d_pre, cs
@@ -794,7 +885,7 @@ class Engine:
         a = torch.empty(shp, device=self.device, dtype=torch.float32)
         stats = self._conv_fwd_with_stats(x, cp, bn, a, self._epi(beta1=e["bias"], act=ACT_LEAKY))
         mv = None if mask is None else _chan_view(mask)
-        self.pointwise(a, y.t, alpha1=stats[0], beta1=stats[1], r1=sc_t, mul=mv, rnd=1)
+        self.pointwise(a, y.t, shadow=y, alpha1=stats[0], beta1=stats[1], r1=sc_t, mul=mv, rnd=1)
         if self.record:
             def bwd():
                 dy = y.grad_read()
@@ -832,8 +923,8 @@ class Engine:
         c_t = torch.empty(shp, device=self.device, dtype=torch.float32)
         stats = self._conv_fwd_with_stats(x, cp, bn, c_t, self._epi(beta1=e["bias"]))
         mv = None if mask is None else _chan_view(mask)
-        self.pointwise(c_t, y.t, alpha1=stats[0], beta1=stats[1], r1=id_t, act=post, mul=f_t if gate is not None else mv,
-                       r2=pcd_t, rnd=1 if rnd else 0)
+        self.pointwise(c_t, y.t, shadow=y if rnd else None, alpha1=stats[0], beta1=stats[1], r1=id_t, act=post,
+                       mul=f_t if gate is not None else mv, r2=pcd_t, rnd=1 if rnd else 0)
         if self.record:
             def bwd():
                 dy = y.grad_read()
@@ -922,7 +1013,7 @@ class Engine:
     def copy(self, src, dst, mask=None):
         """dst = src * mask (a channel slice of a concat buffer)."""
         mv = None if mask is None else _chan_view(mask)
-        self.pointwise(src.t, dst.t, mul=mv, rnd=1 if mask is not None else 0)
+        self.pointwise(src.t, dst.t, shadow=dst, mul=mv, rnd=1 if mask is not None else 0)
         if self.record and src.needs_grad:
             def bwd():
                 g = dst.grad_read()

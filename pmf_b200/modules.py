@@ -304,6 +304,7 @@ class _GraphedPMF:
         self.shape = (n, c_pcd, h, w)
         self.cache = WeightCache(always=True)
         self.cache.precise = _L.get_precision() == "3xtf32"
+        self.cache.h16 = _L.get_precision() == "f16" and mod.training
         self.E = None
         self.version = 0
         self.bwd_captured = False

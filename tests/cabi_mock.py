@@ -501,6 +501,12 @@ def pmfb_pixel_scale(inp, n, h, w, c, pre, act, alpha, beta, r, post, out, o_sn,
     _arr(out, (n, h, w, c), (o_sn, o_sy, o_sx, 1))[...] = v.astype(np.float32)
 
 
+def pmfb_bn_bwd_apply16(*args):
+    """The 16-bit shadow output belongs to the "f16" precision mode, which the engine only enables on CUDA tensors."""
+    assert not args[-2], "the numpy model does not emulate the 16-bit shadow outputs"
+    return pmfb_bn_bwd_apply(*args[:-2], args[-1])
+
+
 _IMPL = {k: v for k, v in globals().items() if k.startswith("pmfb_")}
 
 
