@@ -793,7 +793,9 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
 
     shapes = []
     prev = os.environ.get("PMFB_CUDA_GRAPH")
+    prev_side = os.environ.get("PMFB_WGRAD_STREAM")
     os.environ["PMFB_CUDA_GRAPH"] = "0"
+    os.environ["PMFB_WGRAD_STREAM"] = "0"  # per-launch event timing needs every kernel on the launching stream
     try:
         step_fn()  # eager warm-up (allocator)
         torch.cuda.synchronize()
@@ -809,6 +811,10 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
             os.environ.pop("PMFB_CUDA_GRAPH", None)
         else:
             os.environ["PMFB_CUDA_GRAPH"] = prev
+        if prev_side is None:
+            os.environ.pop("PMFB_WGRAD_STREAM", None)
+        else:
+            os.environ["PMFB_WGRAD_STREAM"] = prev_side
     by = {}
     for (n, f, e0, e1, nb) in recs:
         r = by.setdefault(n, [0, 0.0, 0.0, 0.0])

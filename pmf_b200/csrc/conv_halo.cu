@@ -74,6 +74,72 @@ constexpr int kEpiStats = 16;
 constexpr int kEpiA1 = 32, kEpiRelu = 64, kEpiA2B2 = 128, kEpiR2 = 256;
 constexpr int kHStatsC = 256;  // fused statistics: c_out <= 256 (2 x 256 fp64 accumulators in the unused alpha2/beta2 slots)
 
+// MMA issue loop of conv_fwd_halo_kernel (warp 1), specialised at compile time on the operand kind so that the issuing
+// warp's inner loop carries no per-instruction branch (instruction issue of this warp paces the tensor pipe).
+template <bool F16>
+__device__ __forceinline__ void mma_issue_loop(const HaloK& P, HCtrl* ctrl, uint8_t* a_buf, uint8_t* b_buf, const int b_bytes,
+                                               const uint32_t tmem_base, const int total, const int pitch) {
+    const uint32_t idesc = F16 ? make_idesc_f16(128, (uint32_t)P.n_tile, P.dtype == PMFB_DT_BF16 ? 1u : 0u, 0, 0)
+                               : make_idesc_tf32(128, (uint32_t)P.n_tile, 0, 0);
+    const uint32_t sbo = (uint32_t)pitch * 128u;
+    const uint32_t hi_a = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // bits 32..63 of the A descriptor
+    const uint32_t hi_b = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    const uint32_t lbo_lo = (16u >> 4) << 16;
+    const uint32_t j_step = (uint32_t)(16 * pitch * 128) >> 4;
+    uint32_t a_it = 0, b_it = 0, acc_it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++acc_it) {
+      const uint32_t buf = acc_it % (uint32_t)P.nacc;
+      mbar_wait(&ctrl->tmem_empty[buf], ((acc_it / (uint32_t)P.nacc) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + buf * (uint32_t)(P.mt * P.n_tile);
+      uint32_t accumulate = 0;
+      for (int s = 0; s < P.ks; ++s) {
+        const uint32_t ab = a_it & 1u;
+        mbar_wait(&ctrl->full_a[ab], (a_it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t a_lo0 = ((smem_u32(a_buf + (size_t)ab * P.a_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
+        for (int t = 0; t < P.n_taps; ++t) {
+          const uint32_t st = b_it % (uint32_t)P.nsb;
+          mbar_wait(&ctrl->full_b[st], (b_it / (uint32_t)P.nsb) & 1u);
+          tc_fence_after();
+          const uint32_t b_lo = ((smem_u32(b_buf + (size_t)st * b_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
+          uint32_t a_lo = a_lo0 + (uint32_t)((((P.tap_dh[t] + P.hy) * pitch + P.tap_dw[t] + P.hx) * 128) >> 4);
+          uint32_t d_col = d_base;
+          if (s == P.ks - 1 && P.klast != 4) {  // partial last slab (e.g. 32 channels in a 64-channel 16-bit slab)
+            for (int j = 0; j < P.mt; ++j) {
+              for (int k = 0; k < P.klast; ++k) {
+                const uint64_t ad = (static_cast<uint64_t>(hi_a) << 32) | (a_lo + 2u * k);
+                const uint64_t bd = (static_cast<uint64_t>(hi_b) << 32) | (b_lo + 2u * k);
+                if constexpr (F16) umma_f16_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
+                else umma_tf32_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
+              }
+              a_lo += j_step;
+              d_col += (uint32_t)P.n_tile;
+            }
+          } else {
+            for (int j = 0; j < P.mt; ++j) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = (static_cast<uint64_t>(hi_a) << 32) | (a_lo + 2u * k);
+                const uint64_t bd = (static_cast<uint64_t>(hi_b) << 32) | (b_lo + 2u * k);
+                if constexpr (F16) umma_f16_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
+                else umma_tf32_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
+              }
+              a_lo += j_step;
+              d_col += (uint32_t)P.n_tile;
+            }
+          }
+          accumulate = 1;
+          umma_commit_warp(&ctrl->empty_b[st]);
+          ++b_it;
+        }
+        umma_commit_warp(&ctrl->empty_a[ab]);
+        ++a_it;
+      }
+      umma_commit_warp(&ctrl->tmem_full[buf]);
+    }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
@@ -161,56 +227,8 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
     // UTCHMMA made instruction issue, not the tensor pipe, the limiter); only the tcgen05 instructions are predicated
     // on one lane.  Descriptors are (constant high word | low word), and the low word advances by plain adds:
     // +2 (32 B >> 4) per K step, +(tap row/column offset) per tap, +(16 rows) per stacked tile.
-    const bool f16 = P.dtype != PMFB_DT_F32;
-    const uint32_t idesc = f16 ? make_idesc_f16(128, (uint32_t)P.n_tile, P.dtype == PMFB_DT_BF16 ? 1u : 0u, 0, 0)
-                               : make_idesc_tf32(128, (uint32_t)P.n_tile, 0, 0);
-    const uint32_t sbo = (uint32_t)pitch * 128u;
-    const uint32_t hi_a = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // bits 32..63 of the A descriptor
-    const uint32_t hi_b = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
-    const uint32_t lbo_lo = (16u >> 4) << 16;
-    const uint32_t j_step = (uint32_t)(16 * pitch * 128) >> 4;
-    uint32_t a_it = 0, b_it = 0, acc_it = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++acc_it) {
-      const uint32_t buf = acc_it % (uint32_t)P.nacc;
-      mbar_wait(&ctrl->tmem_empty[buf], ((acc_it / (uint32_t)P.nacc) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + buf * (uint32_t)(P.mt * P.n_tile);
-      uint32_t accumulate = 0;
-      for (int s = 0; s < P.ks; ++s) {
-        const uint32_t ab = a_it & 1u;
-        mbar_wait(&ctrl->full_a[ab], (a_it >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t a_lo0 = ((smem_u32(a_buf + (size_t)ab * P.a_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
-        for (int t = 0; t < P.n_taps; ++t) {
-          const uint32_t st = b_it % (uint32_t)P.nsb;
-          mbar_wait(&ctrl->full_b[st], (b_it / (uint32_t)P.nsb) & 1u);
-          tc_fence_after();
-          const uint32_t b_lo = ((smem_u32(b_buf + (size_t)st * b_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
-          uint32_t a_lo = a_lo0 + (uint32_t)((((P.tap_dh[t] + P.hy) * pitch + P.tap_dw[t] + P.hx) * 128) >> 4);
-          uint32_t d_col = d_base;
-          const int kn = (s == P.ks - 1) ? P.klast : 4;
-          for (int j = 0; j < P.mt; ++j) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < kn) {
-                const uint64_t ad = (static_cast<uint64_t>(hi_a) << 32) | (a_lo + 2u * k);
-                const uint64_t bd = (static_cast<uint64_t>(hi_b) << 32) | (b_lo + 2u * k);
-                if (f16) umma_f16_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
-                else umma_tf32_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
-              }
-            }
-            a_lo += j_step;
-            d_col += (uint32_t)P.n_tile;
-          }
-          accumulate = 1;
-          umma_commit_warp(&ctrl->empty_b[st]);
-          ++b_it;
-        }
-        umma_commit_warp(&ctrl->empty_a[ab]);
-        ++a_it;
-      }
-      umma_commit_warp(&ctrl->tmem_full[buf]);
-    }
+    if (P.dtype != PMFB_DT_F32) mma_issue_loop<true>(P, ctrl, a_buf, b_buf, b_bytes, tmem_base, total, pitch);
+    else mma_issue_loop<false>(P, ctrl, a_buf, b_buf, b_bytes, tmem_base, total, pitch);
   } else {
     // ------------- epilogue: 8 warps; warp pair (q, half) shares TMEM lane quadrant q and alternates 32-column units.
     // Every unit issues its TMEM load and ALL of its residual global loads before the first use (memory-level

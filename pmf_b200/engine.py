@@ -21,6 +21,7 @@ from . import _lib as L
 from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ConvDesc, Epilogue, TmaSrc, View, WeightJob, WgradDesc
 
 BN_EPS_DEFAULT = 1e-5
+H16_MIN_K = int(os.environ.get("PMFB_H16_MIN_K", "64"))
 N_SM = 148
 
 
@@ -589,7 +590,10 @@ class Engine:
         d.o_sn, d.o_sy, d.o_sx = out_t.stride(0), out_t.stride(1), out_t.stride(2)
         d.epi = epi
         d.bn_stats = None
-        if x16 is not None and w16 is not None and not stride2 and c_in % 8 == 0 and L.query("pmfb_conv16_ok", C.byref(d)) == 1:
+        # 16-bit operands pay off from one full 64-channel slab on (a 32-channel layer would fill half of every 128-byte
+        # operand row with zeros: measured slower than the tf32 path)
+        if (x16 is not None and w16 is not None and not stride2 and c_in % 8 == 0 and c_in >= H16_MIN_K
+                and L.query("pmfb_conv16_ok", C.byref(d)) == 1):
             d.x = self._tma_src(x16, c_in, False)
             d.w = w16.data_ptr()
             d.dtype = dt16
@@ -611,7 +615,8 @@ class Engine:
             oh = (h + 2 * cp.pad - cp.dil * (cp.kh - 1) - 1) // cp.stride + 1
             ow = (w + 2 * cp.pad - cp.dil * (cp.kw - 1) - 1) // cp.stride + 1
         assert tuple(out_t.shape) == (n, oh, ow, cp.c_out_p), (cp.name, tuple(out_t.shape), (n, oh, ow, cp.c_out_p))
-        x16 = self._ensure_shadow(x) if (self.h16 and cp.stride == 1 and cp.c_in_p % 8 == 0 and e.get("fwd16") is not None) else None
+        x16 = self._ensure_shadow(x) if (self.h16 and cp.stride == 1 and cp.c_in_p % 8 == 0 and cp.c_in_p >= H16_MIN_K
+                                         and e.get("fwd16") is not None) else None
         fused = self._conv_launch(x.t, cp.c_in_p, cp.stride == 2, e["fwd3" if self.precise else "fwd"], cp.c_out_p, cp.fwd_taps(),
                                   n, oh, ow, out_t, epi, bn_stats=bn_stats, x16=x16, w16=e.get("fwd16"), dt16=L.DT_F16)
         if self.record:
@@ -817,7 +822,7 @@ class Engine:
         cs = self.d64.take(c) if want_colsum else None
         gw, gb = self._pgrad(bn.name + ".weight", bn.weight), self._pgrad(bn.name + ".bias", bn.bias)
         # "f16" mode: the same pass also stores d_pre as bf16, the operand of the kind::f16 dgrad
-        self._dpre16 = torch.empty((n, h, w, c), device=self.device, dtype=torch.bfloat16) if (self.h16 and c % 8 == 0) else None
+        self._dpre16 = torch.empty((n, h, w, c), device=self.device, dtype=torch.bfloat16) if (self.h16 and c % 8 == 0 and c >= H16_MIN_K) else None
         L.call("pmfb_bn_bwd_apply16", C.byref(dyv), C.byref(mulv), C.byref(zv), act_z, C.byref(xv), mean.data_ptr(),
                invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), bn.weight.detach().data_ptr(), red.data_ptr(), leaky_x,
                n, h, w, c, d_pre.data_ptr(), d_pre.stride(0), d_pre.stride(1), d_pre.stride(2), self.R, gw.data_ptr(),
