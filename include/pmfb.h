@@ -45,6 +45,7 @@ typedef enum {
 #define PMFB_DT_F32 0
 #define PMFB_DT_F16 1
 #define PMFB_DT_BF16 2
+#define PMFB_DT_F16_BF16 3 /* A operand (activations) fp16, B operand (weights / output gradients) bf16 */
 
 typedef enum { PMFB_ACT_NONE = 0, PMFB_ACT_RELU = 1, PMFB_ACT_LEAKY = 2, PMFB_ACT_SIGMOID = 3 } pmfb_act;
 
@@ -120,6 +121,10 @@ typedef struct {
   int32_t n_tile;                /* c_out columns per CTA: multiple of 32, <= 256 */
   int32_t ksplit;                /* number of pixel-range splits (grid.z) */
   float* dw;                     /* packed [n_taps][c_in][c_out] */
+  /* PMFB_DT_F32 (fp32 x and dy, kind::tf32) or PMFB_DT_BF16 (bf16 shadows of both, kind::f16; stride-1 layers on the halo
+   * kernel only, c_in and c_out multiples of 8; see pmfb_wgrad16_ok).  x.strides / dy.strides stay in BYTES. */
+  int32_t dtype;
+  int32_t reserved;
 } pmfb_wgrad_desc;
 
 int pmfb_abi_version(void);
@@ -134,6 +139,7 @@ int pmfb_conv_fused_stats_ok(const pmfb_conv_desc* d);
 int pmfb_conv_wgrad(const pmfb_wgrad_desc* d, void* stream);
 /* 1 if pmfb_conv_fwd accepts 16-bit operands (dtype F16 / BF16) for this geometry, else 0. */
 int pmfb_conv16_ok(const pmfb_conv_desc* d);
+int pmfb_wgrad16_ok(const pmfb_wgrad_desc* d);
 
 /* ---------------------------------------------------------------------------------------------
  * Layout / packing kernels

@@ -44,7 +44,7 @@ class WgradDesc(C.Structure):
     _fields_ = [("x", TmaSrc), ("dy", TmaSrc), ("c_in", i32), ("c_out", i32), ("n_taps", i32),
                 ("tap_dc", i32 * MAX_TAPS), ("tap_dw", i32 * MAX_TAPS), ("tap_dp", i32 * MAX_TAPS),
                 ("tap_dh", i32 * MAX_TAPS), ("n_batch", i32), ("out_h", i32), ("out_w", i32), ("ptile_w", i32),
-                ("ptile_h", i32), ("n_tile", i32), ("ksplit", i32), ("dw", C.c_void_p)]
+                ("ptile_h", i32), ("n_tile", i32), ("ksplit", i32), ("dw", C.c_void_p), ("dtype", i32), ("reserved", i32)]
 
 
 class WeightJob(C.Structure):
@@ -64,6 +64,7 @@ _SIGNATURES = {
     "pmfb_conv_fused_stats_ok": ([C.POINTER(ConvDesc)], C.c_int),
     "pmfb_conv_wgrad": ([C.POINTER(WgradDesc), vp], C.c_int),
     "pmfb_conv16_ok": ([C.POINTER(ConvDesc)], C.c_int),
+    "pmfb_wgrad16_ok": ([C.POINTER(WgradDesc)], C.c_int),
     "pmfb_pointwise16": ([VP, vp, i64, i64, i64, i32, i32, i32, i32, C.POINTER(Epilogue), vp, i32, vp], C.c_int),
     "pmfb_convert16": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
     "pmfb_bn_bwd_apply16": ([VP, VP, VP, i32, VP, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i64, i64, i64,

@@ -79,7 +79,8 @@ constexpr int kHStatsC = 256;  // fused statistics: c_out <= 256 (2 x 256 fp64 a
 template <bool F16>
 __device__ __forceinline__ void mma_issue_loop(const HaloK& P, HCtrl* ctrl, uint8_t* a_buf, uint8_t* b_buf, const int b_bytes,
                                                const uint32_t tmem_base, const int total, const int pitch) {
-    const uint32_t idesc = F16 ? make_idesc_f16(128, (uint32_t)P.n_tile, P.dtype == PMFB_DT_BF16 ? 1u : 0u, 0, 0)
+    const uint32_t idesc = F16 ? make_idesc_f16(128, (uint32_t)P.n_tile, P.dtype == PMFB_DT_BF16 ? 1u : 0u,
+                                                (P.dtype == PMFB_DT_BF16 || P.dtype == PMFB_DT_F16_BF16) ? 1u : 0u, 0, 0)
                                : make_idesc_tf32(128, (uint32_t)P.n_tile, 0, 0);
     const uint32_t sbo = (uint32_t)pitch * 128u;
     const uint32_t hi_a = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // bits 32..63 of the A descriptor
@@ -654,7 +655,7 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   uint64_t wdims[3] = {(uint64_t)d->c_in, (uint64_t)d->c_out, (uint64_t)n_slabs};
   uint64_t wstr[2] = {(uint64_t)d->c_in * esz, (uint64_t)d->c_in * d->c_out * esz};
   uint32_t boxw[3] = {(uint32_t)P.kslab, (uint32_t)n_tile, 1};
-  rc = h16 ? make_tmap_16(&tmw, d->w, 3, wdims, wstr, boxw, d->dtype == PMFB_DT_BF16) : make_tmap_f32(&tmw, d->w, 3, wdims, wstr, boxw);
+  rc = h16 ? make_tmap_16(&tmw, d->w, 3, wdims, wstr, boxw, d->dtype != PMFB_DT_F16) : make_tmap_f32(&tmw, d->w, 3, wdims, wstr, boxw);
   if (rc) return rc;
 
   CUtensorMap tmo = tmw;  // placeholder when the direct-store path is used

@@ -422,6 +422,13 @@ extern "C" int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream) {
   return PMFB_OK;
 }
 
+extern "C" int pmfb_wgrad16_ok(const pmfb_wgrad_desc* d) {
+  if (!d || d->n_taps < 1 || d->n_taps > PMFB_MAX_TAPS || d->c_in % 8 || d->c_out % 8) return 0;
+  const char* e = getenv("PMFB_WGRAD_V1");
+  if (e && atoi(e)) return 0;
+  return wgrad_halo_eligible(d) ? 1 : 0;
+}
+
 extern "C" int pmfb_conv_wgrad(const pmfb_wgrad_desc* d, void* stream) {
   if (!d) return fail(PMFB_ERR_INVALID, "null desc");
   if (d->n_taps < 1 || d->n_taps > PMFB_MAX_TAPS) return fail(PMFB_ERR_INVALID, "n_taps=%d", d->n_taps);
@@ -434,6 +441,7 @@ extern "C" int pmfb_conv_wgrad(const pmfb_wgrad_desc* d, void* stream) {
     }
     if (!force_v1 && wgrad_halo_eligible(d)) return launch_wgrad_halo(d, stream);
   }
+  if (d->dtype != PMFB_DT_F32) return fail(PMFB_ERR_INVALID, "conv_wgrad: bf16 operands are only supported on the stride-1 halo kernel (query pmfb_wgrad16_ok)");
   if (d->ptile_w * d->ptile_h != 32) return fail(PMFB_ERR_INVALID, "ptile_w*ptile_h must be 32");
   if (d->n_tile < 32 || d->n_tile > 256 || d->n_tile % 32)
     return fail(PMFB_ERR_INVALID, "n_tile=%d must be a multiple of 32 in [32,256]", d->n_tile);

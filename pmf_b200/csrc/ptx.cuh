@@ -231,12 +231,12 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t M, uint32_
 }
 
 // Instruction descriptor for kind::f16 with fp32 accumulation: a_format / b_format 0 = F16, 1 = BF16.
-__host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t bf16, uint32_t a_mn_major,
-                                                            uint32_t b_mn_major) {
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t a_bf16, uint32_t b_bf16,
+                                                            uint32_t a_mn_major, uint32_t b_mn_major) {
   uint32_t d = 0;
   d |= 1u << 4;
-  d |= (bf16 & 1u) << 7;
-  d |= (bf16 & 1u) << 10;
+  d |= (a_bf16 & 1u) << 7;
+  d |= (b_bf16 & 1u) << 10;
   d |= (a_mn_major & 1u) << 15;
   d |= (b_mn_major & 1u) << 16;
   d |= ((N >> 3) & 0x3Fu) << 17;

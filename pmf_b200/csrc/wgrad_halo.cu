@@ -48,6 +48,7 @@ struct WHaloK {
   int grp_cnt[PMFB_MAX_TAPS];
   int grp_tap[PMFB_MAX_TAPS][4];   // weight-gradient slab of each packed tap
   int a_blk_bytes, a_span, b_blk_bytes, stage_bytes, stages, tmem_cols;
+  int dtype, kslab;  // PMFB_DT_F32 (tf32, 32-channel boxes) or PMFB_DT_BF16 (kind::f16, 64-channel boxes)
   float* dw;
 };
 
@@ -69,8 +70,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_con
   const int cg = grp / P.n_blocks, nb = grp - cg * P.n_blocks;
   const int g_begin = ts * P.gps, g_end = min(g_begin + P.gps, P.n_groups);
   const int ci0 = cg * 128, n0 = nb * P.n_tile;
-  int nblk_a = (P.c_in - ci0 + 31) / 32;
-  if (nblk_a > 4) nblk_a = 4;
+  int nblk_a = (P.c_in - ci0 + P.kslab - 1) / P.kslab;
+  if (nblk_a > 128 / P.kslab) nblk_a = 128 / P.kslab;
   const int total_tiles = P.tiles_x * P.tiles_y * P.n_batch;
   const int iters = (total_tiles - sidx + P.split - 1) / P.split;  // tiles sidx, sidx+split, ...
 
@@ -110,11 +111,42 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_con
           uint8_t* b_s = a_s + (size_t)P.a_span;
           mbar_expect_tx(&ctrl->full[s], tx_bytes);
           for (int i = 0; i < nblk_a; ++i)
-            tma_load_5d(a_s + (size_t)i * P.a_blk_bytes, &tmx, &ctrl->full[s], ci0 + i * 32, x0 - P.hx, 0, y0 - P.hy, n_img);
+            tma_load_5d(a_s + (size_t)i * P.a_blk_bytes, &tmx, &ctrl->full[s], ci0 + i * P.kslab, x0 - P.hx, 0, y0 - P.hy, n_img);
           for (int j = 0; j < P.nblk_b; ++j)
-            tma_load_5d(b_s + (size_t)j * P.b_blk_bytes, &tmdy, &ctrl->full[s], n0 + j * 32, x0, 0, y0, n_img);
+            tma_load_5d(b_s + (size_t)j * P.b_blk_bytes, &tmdy, &ctrl->full[s], n0 + j * P.kslab, x0, 0, y0, n_img);
         }
       }
+    } else if (warp == 1 && P.dtype != PMFB_DT_F32) {
+      // ---- 16-bit operands (bf16 x bf16, kind::f16, K = 16 pixels per UMMA).  Both operands MN-major with the plain
+      // 128B swizzle: a pixel row holds 64 channels (128 B), a swizzle atom is 8 pixel rows (1024 B).  One K step spans two
+      // atoms: for dy (dense 8x8 tile) they are 1024 B apart, for the x halo tile two consecutive 8-pixel tile rows, i.e.
+      // pitch*128 B apart -- the stride-byte-offset; the leading-byte-offset steps over 64-channel blocks.
+      const uint32_t idesc = make_idesc_f16(128, (uint32_t)P.n_tile, 1, 1, 1, 1);
+      const uint32_t hi_a = ((((uint32_t)pitch * 128u) >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      const uint32_t hi_b = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      const uint32_t lbo_a = (((uint32_t)P.a_blk_bytes >> 4) & 0x3FFFu) << 16;
+      const uint32_t lbo_b = (((uint32_t)P.b_blk_bytes >> 4) & 0x3FFFu) << 16;
+      const uint32_t a_kstep = (uint32_t)(2 * pitch * 128) >> 4;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % P.stages;
+        mbar_wait(&ctrl->full[s], (uint32_t)(it / P.stages) & 1u);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(tiles + (size_t)s * P.stage_bytes);
+        const uint32_t a_lo00 = ((a_addr & 0x3FFFFu) >> 4) | lbo_a;
+        const uint32_t b_lo0 = (((a_addr + (uint32_t)P.a_span) & 0x3FFFFu) >> 4) | lbo_b;
+        for (int t = g_begin; t < g_end; ++t) {
+          const uint32_t a_tap = a_lo00 + (uint32_t)((P.grp_off[t] * 128) >> 4);
+          const uint32_t d_col = tmem_base + (uint32_t)((t - g_begin) * P.n_tile);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {  // two tile rows (16 pixels) per K step
+            const uint64_t ad = (static_cast<uint64_t>(hi_a) << 32) | (a_tap + (uint32_t)ks * a_kstep);
+            const uint64_t bd = (static_cast<uint64_t>(hi_b) << 32) | (b_lo0 + 128u * ks);
+            umma_f16_warp(d_col, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit_warp(&ctrl->empty[s]);
+      }
+      umma_commit_warp(&ctrl->tmem_full);
     } else if (warp == 1) {
       // whole warp, uniform descriptors, one elected lane issues (see conv_halo.cu)
       const uint32_t idesc = make_idesc_tf32(128, (uint32_t)P.n_tile, 1, 1);
@@ -196,6 +228,11 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
   }
   WHaloK P;
   P.n_taps = d->n_taps;
+  P.dtype = d->dtype;
+  const bool h16 = d->dtype != PMFB_DT_F32;
+  if (h16 && d->dtype != PMFB_DT_BF16) return fail(PMFB_ERR_INVALID, "wgrad halo: 16-bit operands must be bf16");
+  if (h16 && (d->c_in % 8 || d->c_out % 8)) return fail(PMFB_ERR_INVALID, "wgrad halo: bf16 operands need c_in, c_out multiples of 8");
+  P.kslab = h16 ? 64 : 32;
   P.hx = P.hy = 0;
   for (int i = 0; i < PMFB_MAX_TAPS; ++i) {
     P.tap_dw[i] = d->tap_dw[i];
@@ -221,7 +258,7 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
     const char* e = getenv("PMFB_WGRAD_PACK");
     pack_mode = e ? atoi(e) : 1;
   }
-  P.packed = (pack_mode && d->c_in <= 32 && d->n_taps > 1) ? 1 : 0;
+  P.packed = (pack_mode && d->c_in <= 32 && d->n_taps > 1 && !h16) ? 1 : 0;
   P.n_groups = 0;
   {
     int off[PMFB_MAX_TAPS], used[PMFB_MAX_TAPS];
@@ -267,8 +304,9 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
   // max(MMA, L2->SM fill) time.
   const int c_out16 = (d->c_out + 15) & ~15;
   const int c_groups = (d->c_in + 127) / 128;
-  int nblk_a_max = (d->c_in + 31) / 32;
-  if (nblk_a_max > 4) nblk_a_max = 4;
+  int nblk_a_max = (d->c_in + P.kslab - 1) / P.kslab;
+  if (nblk_a_max > 128 / P.kslab) nblk_a_max = 128 / P.kslab;
+  const int blocks_m = 128 / P.kslab;  // operand blocks the M = 128 descriptor spans
   const int a_blk = (rows * pitch * 128 + 1023) & ~1023;
   int n_tile = 0, gps = P.n_groups;
   {
@@ -286,11 +324,11 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
       if (bal < nt) nt = bal;
       const int tsp = (P.n_groups + g - 1) / g;
       // shared memory: at least two (x halo blocks + dy blocks) stages, three preferred
-      const int stage_b = nblk_a_max * a_blk + ((nt + 31) / 32) * 8192;
-      const int st_fit = (kWSmemBudget - kWCtrlBytes - (4 - nblk_a_max) * a_blk) / stage_b;
+      const int stage_b = nblk_a_max * a_blk + ((nt + P.kslab - 1) / P.kslab) * 8192;
+      const int st_fit = (kWSmemBudget - kWCtrlBytes - (blocks_m - nblk_a_max) * a_blk) / stage_b;
       if (st_fit < 2) continue;
-      const double mma = (double)c_groups * nbk * P.n_groups * 8.0 * (128.0 + nt) * 0.5;
-      const double fill = (double)c_groups * nbk * tsp * (nblk_a_max * (double)a_blk + ((nt + 31) / 32) * 8192.0) / 43.0;
+      const double mma = (double)c_groups * nbk * P.n_groups * (h16 ? 4.0 : 8.0) * (128.0 + nt) * 0.5;
+      const double fill = (double)c_groups * nbk * tsp * (nblk_a_max * (double)a_blk + ((nt + P.kslab - 1) / P.kslab) * 8192.0) / 43.0;
       const double cost = ((mma > fill ? mma : fill) + 0.25 * (mma > fill ? fill : mma)) * (st_fit < 3 ? 1.15 : 1.0);
       if (cost < best) {
         best = cost;
@@ -325,7 +363,7 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
   if (split < 1) split = 1;
   if (split > total_tiles) split = (int)total_tiles;
   P.split = split;
-  P.nblk_b = (n_tile + 31) / 32;
+  P.nblk_b = (n_tile + P.kslab - 1) / P.kslab;
   P.a_blk_bytes = (rows * pitch * 128 + 1023) & ~1023;
   P.b_blk_bytes = 64 * 128;
   // Only the channel blocks that exist are loaded and given shared memory; the A descriptor still spans four blocks
@@ -333,7 +371,7 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
   // those accumulator rows are never flushed, and every D row depends on its own A row only.
   P.a_span = nblk_a_max * P.a_blk_bytes;
   P.stage_bytes = P.a_span + P.nblk_b * P.b_blk_bytes;
-  const int tail_pad = (4 - nblk_a_max) * P.a_blk_bytes;
+  const int tail_pad = (blocks_m - nblk_a_max) * P.a_blk_bytes;
   int stages = (kWSmemBudget - kWCtrlBytes - tail_pad) / P.stage_bytes;
   if (stages > kWMaxStages) stages = kWMaxStages;
   if (stages < 2) return fail(PMFB_ERR_INVALID, "wgrad halo: stage of %d bytes does not fit twice", P.stage_bytes);
@@ -344,11 +382,13 @@ int launch_wgrad_halo(const pmfb_wgrad_desc* d, void* stream) {
   P.dw = d->dw;
 
   CUtensorMap tmx, tmdy;
-  uint32_t boxx[5] = {32, (uint32_t)pitch, 1, (uint32_t)rows, 1};
-  int rc = make_tmap_f32(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, boxx, true);
+  uint32_t boxx[5] = {(uint32_t)P.kslab, (uint32_t)pitch, 1, (uint32_t)rows, 1};
+  int rc = h16 ? make_tmap_16(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, boxx, true)
+               : make_tmap_f32(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, boxx, true);
   if (rc) return rc;
-  uint32_t boxy[5] = {32, 8, 1, 8, 1};
-  rc = make_tmap_f32(&tmdy, d->dy.ptr, 5, d->dy.dims, d->dy.strides, boxy, true);
+  uint32_t boxy[5] = {(uint32_t)P.kslab, 8, 1, 8, 1};
+  rc = h16 ? make_tmap_16(&tmdy, d->dy.ptr, 5, d->dy.dims, d->dy.strides, boxy, true)
+           : make_tmap_f32(&tmdy, d->dy.ptr, 5, d->dy.dims, d->dy.strides, boxy, true);
   if (rc) return rc;
 
   const size_t smem = (size_t)kWCtrlBytes + (size_t)stages * P.stage_bytes + tail_pad + 1024;

@@ -22,6 +22,7 @@ from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ConvDesc, Epilogue
 
 BN_EPS_DEFAULT = 1e-5
 H16_MIN_K = int(os.environ.get("PMFB_H16_MIN_K", "64"))
+H16_WGRAD = os.environ.get("PMFB_H16_WGRAD", "1") != "0"
 N_SM = 148
 
 
@@ -731,6 +732,17 @@ class Engine:
             pairs = ((x_hi, dy_hi), (x_hi, dy_lo), (x_lo, dy_hi))
         else:
             pairs = ((x.t, d_pre),)
+            # "f16" mode: bf16 shadows of both operands (kind::f16, K = 16 pixels per UMMA) where the library takes them
+            if (self.h16 and H16_WGRAD and d16 is not None and cp.stride == 1 and cp.c_in_p % 8 == 0 and cp.c_in_p >= H16_MIN_K
+                    and cp.c_out_p >= H16_MIN_K):
+                d.x = self._tma_src(x.t, cp.c_in_p, False)
+                d.dy = self._tma_src(d_pre, cp.c_out_p)
+                if L.query("pmfb_wgrad16_ok", C.byref(d)) == 1:
+                    xb = torch.empty(x.t.shape, device=self.device, dtype=torch.bfloat16)
+                    L.call("pmfb_convert16", C.byref(_view(x.t)), n, h, w, cp.c_in_p, xb.data_ptr(), xb.stride(0), xb.stride(1),
+                           xb.stride(2), L.DT_BF16, self.st)
+                    pairs = ((xb, d16),)
+                    d.dtype = L.DT_BF16
         for xa, dya in pairs:
             d.x = self._tma_src(xa, cp.c_in_p, cp.stride == 2)
             d.dy = self._tma_src(dya, cp.c_out_p)
