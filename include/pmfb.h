@@ -196,11 +196,13 @@ int pmfb_unpack_wgrad(const float* packed, int32_t c_out, int32_t c_in, int32_t 
 int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n, int32_t h,
                    int32_t w, int32_t c, const pmfb_epilogue* epi, void* stream);
 
-/* pmfb_pointwise that ALSO stores the result as a 16-bit shadow (out16: same element strides and channel offset as out;
- * dtype16 = PMFB_DT_F16 or PMFB_DT_BF16; values saturate to the fp16 range): the BN-apply pass that produces a conv input
- * writes the operand the kind::f16 convolution will read in the same pass.  out16 == NULL: identical to pmfb_pointwise. */
+/* pmfb_pointwise that ALSO stores the result as 16-bit shadows (same element strides and channel offset as out): out16 in
+ * dtype16 = PMFB_DT_F16 or PMFB_DT_BF16 (fp16 values saturate to the fp16 range) and / or out16_bf16 in bf16.  The BN-apply
+ * pass that produces a conv input writes the operands the kind::f16 convolution (fp16) and weight gradient (bf16) will read
+ * in the same pass.  Both NULL: identical to pmfb_pointwise. */
 int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n, int32_t h,
-                     int32_t w, int32_t c, const pmfb_epilogue* epi, void* out16, int32_t dtype16, void* stream);
+                     int32_t w, int32_t c, const pmfb_epilogue* epi, void* out16, int32_t dtype16, void* out16_bf16,
+                     void* stream);
 
 /* 16-bit shadow of an fp32 NHWC view (c % 8 == 0; out16 has element strides o_sn / o_sy / o_sx, channel stride 1). */
 int pmfb_convert16(const pmfb_view* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out16, int64_t o_sn, int64_t o_sy,
@@ -241,7 +243,8 @@ int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view
                       int32_t round_out, float* dgamma, float* dbeta, double* colsum, float* g_out, int64_t g_sn,
                       int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* stream);
 
-/* pmfb_bn_bwd_apply that also stores dx as bf16 (dx16: same strides as dx): the operand of the kind::f16 dgrad. */
+/* pmfb_bn_bwd_apply that also stores dx as bf16 (dx16: same strides d_sn / d_sy / d_sx as dx): the operand of the
+ * kind::f16 dgrad and weight gradient.  dx may then be NULL (only the bf16 copy is stored). */
 int pmfb_bn_bwd_apply16(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z,
                         const pmfb_view* x, const float* mean, const float* invstd, const float* alpha,
                         const float* beta, const float* gamma, const double* red, int32_t leaky_x, int32_t n,

@@ -65,7 +65,7 @@ _SIGNATURES = {
     "pmfb_conv_wgrad": ([C.POINTER(WgradDesc), vp], C.c_int),
     "pmfb_conv16_ok": ([C.POINTER(ConvDesc)], C.c_int),
     "pmfb_wgrad16_ok": ([C.POINTER(WgradDesc)], C.c_int),
-    "pmfb_pointwise16": ([VP, vp, i64, i64, i64, i32, i32, i32, i32, C.POINTER(Epilogue), vp, i32, vp], C.c_int),
+    "pmfb_pointwise16": ([VP, vp, i64, i64, i64, i32, i32, i32, i32, C.POINTER(Epilogue), vp, i32, vp, vp], C.c_int),
     "pmfb_convert16": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
     "pmfb_bn_bwd_apply16": ([VP, VP, VP, i32, VP, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i64, i64, i64,
                              i32, vp, vp, vp, vp, i64, i64, i64, i32, vp, vp], C.c_int),

@@ -244,7 +244,8 @@ struct BnBwdApplyF {
   int C, leaky_x, round_out;
   PV dx;
   PV g_out;
-  unsigned short* dx16;  // optional bf16 copy of dx (same element offsets): the operand of the kind::f16 dgrad
+  unsigned short* dx16;  // optional bf16 copy of dx (same element offsets): the operand of the kind::f16 dgrad / wgrad
+  int write_dx32;        // 0: only the bf16 copy is stored (dx.p is then a placeholder base used for offsets only)
   struct Loaded { typename GradIn<MUL, ZST>::Loaded i; float4 e[GACC ? 1 : 0]; };
   struct Consts { typename GradIn<MUL, ZST>::Consts i; float4 gi, m1, m2; };
   __device__ __forceinline__ void prep(int c, Consts& k) const {
@@ -289,7 +290,7 @@ struct BnBwdApplyF {
     }
     if (dx.p) {
       float* dp = const_cast<float*>(pv_at(dx, pix, hw, w, c));
-      *reinterpret_cast<float4*>(dp) = d;
+      if (write_dx32) *reinterpret_cast<float4*>(dp) = d;
       if (dx16) {
         const __nv_bfloat162 a = __floats2bfloat162_rn(d.x, d.y), b = __floats2bfloat162_rn(d.z, d.w);
         uint2 r;
@@ -492,8 +493,10 @@ static int bn_bwd_apply_t(const ApplyArgs& A) {
   f.C = A.c;
   f.leaky_x = A.leaky_x;
   f.round_out = A.round_out;
-  f.dx = pv_out(A.dx, A.d_sn, A.d_sy, A.d_sx, A.h, A.w);
+  // dx == NULL with dx16 set: only the bf16 copy is wanted; a placeholder base keeps the offset arithmetic
+  f.dx = pv_out(A.dx ? A.dx : (A.dx16 ? reinterpret_cast<float*>(uintptr_t(1024)) : nullptr), A.d_sn, A.d_sy, A.d_sx, A.h, A.w);
   f.dx16 = static_cast<unsigned short*>(A.dx16);
+  f.write_dx32 = A.dx ? 1 : 0;
   f.g_out = pv_out(A.g_out, A.g_sn, A.g_sy, A.g_sx, A.h, A.w);
   RedGrid g = red_grid(chan_reduce_kernel<1, F>, npix, A.c / 4, 1);
   chan_reduce_kernel<1, F><<<g.grid, kRedThreads, 0, (cudaStream_t)A.stream>>>(f, (unsigned)npix, (unsigned)(A.h * A.w), (unsigned)A.w,
@@ -534,7 +537,8 @@ extern "C" int pmfb_bn_bwd_apply16(const pmfb_view* dy, const pmfb_view* mul, co
                                    int32_t h, int32_t w, int32_t c, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
                                    int32_t round_out, float* dgamma, float* dbeta, double* colsum, float* g_out, int64_t g_sn,
                                    int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* dx16, void* stream) {
-  REQ(!dx16 || (dx && (reinterpret_cast<uintptr_t>(dx16) & 7) == 0), "bn_bwd_apply16: dx16 needs dx and 8-byte alignment");
+  REQ(!dx16 || (reinterpret_cast<uintptr_t>(dx16) & 7) == 0, "bn_bwd_apply16: dx16 must be 8-byte aligned");
+  REQ(dx || !dx16 || (((d_sn | d_sy | d_sx) % 4) == 0), "bn_bwd_apply16: bad dx16 strides");
   REQ(c > 0 && c % 4 == 0, "bn_bwd_apply: c=%d", c);
   REQ(!mean || (gamma && red), "bn_bwd_apply: BN backward needs gamma and red");
   REQ(!leaky_x || (x && x->ptr), "bn_bwd_apply: leaky_x needs x");

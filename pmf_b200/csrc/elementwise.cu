@@ -74,6 +74,7 @@ struct PWParams {
   int act, round_out;
   unsigned short* out16;  // optional 16-bit shadow of the result (same element offsets as out)
   int dt16;
+  unsigned short* out16b;  // optional second shadow, always bf16 (the wgrad operand)
 };
 
 // OPS (bit 0: r1, bit 1: mul, bit 2: r2) is a compile-time mask of the per-pixel operands: the common launches (BN apply,
@@ -119,6 +120,7 @@ pointwise_kernel(PWParams P, unsigned npix, unsigned hw, unsigned w, int c4, int
         float* op = const_cast<float*>(pw_at(P.out, p, hw, w, c));
         *reinterpret_cast<float4*>(op) = o;
         if (P.out16) *reinterpret_cast<uint2*>(P.out16 + (op - P.out.p)) = pack16(o, P.dt16);
+        if (P.out16b) *reinterpret_cast<uint2*>(P.out16b + (op - P.out.p)) = pack16(o, PMFB_DT_BF16);
       }
     }
   }
@@ -673,12 +675,13 @@ static inline PWV pwv(const float* p, long long sn, long long sy, long long sx, 
 
 extern "C" int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n,
                               int32_t h, int32_t w, int32_t c, const pmfb_epilogue* epi, void* stream) {
-  return pmfb_pointwise16(in, out, o_sn, o_sy, o_sx, n, h, w, c, epi, nullptr, PMFB_DT_F16, stream);
+  return pmfb_pointwise16(in, out, o_sn, o_sy, o_sx, n, h, w, c, epi, nullptr, PMFB_DT_F16, nullptr, stream);
 }
 
 extern "C" int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n,
                                 int32_t h, int32_t w, int32_t c, const pmfb_epilogue* epi, void* out16, int32_t dtype16,
-                                void* stream) {
+                                void* out16_bf16, void* stream) {
+  REQ(!out16_bf16 || (reinterpret_cast<uintptr_t>(out16_bf16) & 7) == 0, "pointwise16: the bf16 output must be 8-byte aligned");
   REQ(epi && c > 0 && c % 4 == 0, "pointwise: c=%d must be a positive multiple of 4", c);
   REQ(!out16 || ((dtype16 == PMFB_DT_F16 || dtype16 == PMFB_DT_BF16) && (reinterpret_cast<uintptr_t>(out16) & 7) == 0),
       "pointwise16: the 16-bit output must be 8-byte aligned, dtype F16 or BF16");
@@ -704,6 +707,7 @@ extern "C" int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, i
   P.round_out = E.round_out;
   P.out16 = static_cast<unsigned short*>(out16);
   P.dt16 = dtype16;
+  P.out16b = static_cast<unsigned short*>(out16_bf16);
   const int ops = (P.r1.p ? 1 : 0) | (P.mul.p ? 2 : 0) | (P.r2.p ? 4 : 0);
   const cudaStream_t st = (cudaStream_t)stream;
   switch (ops) {

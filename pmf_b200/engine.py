@@ -56,7 +56,7 @@ def _p(t):
 
 class Act:
     """An NHWC activation: ``t`` is a (N,H,W,C) torch view; slices share the root's gradient buffer."""
-    __slots__ = ("t", "root", "c0", "needs_grad", "_round_grad", "grad", "gcov", "h", "hcov")
+    __slots__ = ("t", "root", "c0", "needs_grad", "_round_grad", "grad", "gcov", "h", "hcov", "hb", "hbcov")
 
     def __init__(self, t, root=None, c0=0, needs_grad=True):
         self.t = t
@@ -68,27 +68,33 @@ class Act:
         self.gcov = []           # root only: channel intervals of grad already written
         self.h = None            # root only ("f16" mode): fp16 shadow of t, the operand of the kind::f16 convolutions
         self.hcov = []           # root only: channel intervals of the shadow that hold current values
+        self.hb = None           # root only ("f16" mode, recording): bf16 shadow of t, the x operand of the bf16 wgrad
+        self.hbcov = []
 
     # ---- 16-bit shadow ("f16" precision mode)
-    def shadow(self):
-        """fp16 view matching self.t, or None when this buffer has no shadow."""
+    def shadow(self, bf16=False):
+        """fp16 (or bf16) view matching self.t, or None when this buffer has no such shadow."""
+        buf = self.root.hb if bf16 else self.root.h
+        return None if buf is None else buf[..., self.c0:self.c0 + self.c]
+
+    def shadow_valid(self, bf16=False):
+        a, b = self.c0, self.c0 + self.c
+        return any(x <= a and b <= y for (x, y) in (self.root.hbcov if bf16 else self.root.hcov))
+
+    def shadow_mark(self, bf16=False):
+        a, b = self.c0, self.c0 + self.c
         r = self.root
-        return None if r.h is None else r.h[..., self.c0:self.c0 + self.c]
-
-    def shadow_valid(self):
-        a, b = self.c0, self.c0 + self.c
-        return any(x <= a and b <= y for (x, y) in self.root.hcov)
-
-    def shadow_mark(self):
-        a, b = self.c0, self.c0 + self.c
-        iv = sorted(self.root.hcov + [(a, b)])
+        iv = sorted((r.hbcov if bf16 else r.hcov) + [(a, b)])
         merged = [iv[0]]
         for (x, y) in iv[1:]:
             if x <= merged[-1][1]:
                 merged[-1] = (merged[-1][0], max(merged[-1][1], y))
             else:
                 merged.append((x, y))
-        self.root.hcov = merged
+        if bf16:
+            r.hbcov = merged
+        else:
+            r.hcov = merged
 
     @property
     def shape(self):
@@ -460,20 +466,23 @@ class Engine:
 
     def new(self, n, h, w, c, needs_grad=True):
         a = Act(torch.empty((n, h, w, c), device=self.device, dtype=torch.float32), needs_grad=needs_grad)
-        if self.h16 and c % 8 == 0:
+        if self.h16 and c % 8 == 0 and c >= H16_MIN_K:
             a.h = torch.empty((n, h, w, c), device=self.device, dtype=torch.float16)
+            if self.record and H16_WGRAD:
+                a.hb = torch.empty((n, h, w, c), device=self.device, dtype=torch.bfloat16)
         return a
 
-    def _ensure_shadow(self, x):
-        """fp16 shadow view of Act x with current values (converted here if its producer did not write it), or None."""
-        sh = x.shadow()
+    def _ensure_shadow(self, x, bf16=False):
+        """fp16 (bf16) shadow view of Act x with current values (converted here if its producer did not write it), or
+        None when the buffer has no such shadow."""
+        sh = x.shadow(bf16)
         if sh is None:
             return None
-        if not x.shadow_valid():
+        if not x.shadow_valid(bf16):
             n, h, w, c = x.shape
             L.call("pmfb_convert16", C.byref(_view(x.t)), n, h, w, c, sh.data_ptr(), sh.stride(0), sh.stride(1), sh.stride(2),
-                   L.DT_F16, self.st)
-            x.shadow_mark()
+                   L.DT_BF16 if bf16 else L.DT_F16, self.st)
+            x.shadow_mark(bf16)
         return sh
 
     def _epi(self, alpha1=None, beta1=None, alpha2=None, beta2=None, r1=None, mul=None, r2=None, act=ACT_NONE, rnd=0):
@@ -495,9 +504,12 @@ class Engine:
         sh = shadow.shadow() if (self.h16 and shadow is not None) else None
         if sh is not None:
             assert tuple(sh.stride()) == tuple(dst.stride()), (sh.stride(), dst.stride())
+            shb = shadow.shadow(True)
             L.call("pmfb_pointwise16", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
-                   C.byref(e), sh.data_ptr(), L.DT_F16, self.st)
+                   C.byref(e), sh.data_ptr(), L.DT_F16, _p(shb), self.st)
             shadow.shadow_mark()
+            if shb is not None:
+                shadow.shadow_mark(True)
             return
         L.call("pmfb_pointwise", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
                C.byref(e), self.st)
@@ -571,6 +583,8 @@ class Engine:
         Precise mode: ``w_packed`` is the [hi|lo|hi] split packing over 3*roundup(c_in,32) channels and x is split here.
         "f16" mode: ``x16`` / ``w16`` are 16-bit shadows of x_t / w_packed (dt16 = DT_F16 or DT_BF16); they are used when the
         library accepts 16-bit operands for this geometry (pmfb_conv16_ok), else the fp32 operands."""
+        if x_t is None:  # "f16" mode backward: only the bf16 copy of the output gradient was stored
+            assert x16 is not None and w16 is not None and not stride2
         if self.precise:
             c3 = 3 * _rup(c_in, 32)
             x_t = self.split(x_t, 0)
@@ -578,7 +592,7 @@ class Engine:
                 taps = [((dc // c_in) * c3, dw, dp, dh, wi) for (dc, dw, dp, dh, wi) in taps]
             c_in = c3
         d = ConvDesc()
-        d.x = self._tma_src(x_t, c_in, stride2)
+        d.x = self._tma_src(x_t if x_t is not None else x16, c_in, stride2)
         d.w = w_packed.data_ptr()
         d.c_in, d.c_out, d.n_taps = c_in, c_out, len(taps)
         for i, (dc, dw, dp, dh, wi) in enumerate(taps):
@@ -598,6 +612,8 @@ class Engine:
             d.x = self._tma_src(x16, c_in, False)
             d.w = w16.data_ptr()
             d.dtype = dt16
+        elif x_t is None:
+            raise L.PmfbError("pmf_b200: the library refused 16-bit operands for a layer planned on the bf16 backward path")
         fused = False
         if bn_stats is not None and L.query("pmfb_conv_fused_stats_ok", C.byref(d)) == 1:
             d.bn_stats = bn_stats.data_ptr()
@@ -691,11 +707,11 @@ class Engine:
     def _conv_bwd(self, x, cp, d_pre):
         """wgrad (+ dgrad into x's gradient) of out = conv(x) given d_pre = dL/d(conv output), tf32-rounded."""
         d16, self._dpre16 = self._dpre16, None  # bf16 shadow of d_pre left by _bn_backward for THIS layer (or None)
-        if d16 is not None and tuple(d16.shape) != tuple(d_pre.shape):
+        if d16 is not None and d_pre is not None and tuple(d16.shape) != tuple(d_pre.shape):
             d16 = None
         e = self.cache.get(cp, True, self.st)
         n, h, w, _ = x.shape
-        _, oh, ow, co = d_pre.shape
+        _, oh, ow, co = (d_pre if d_pre is not None else d16).shape
         assert co == cp.c_out_p
         # ---- wgrad -> packed [taps][c_in_p][c_out_p] (split-K atomics; buffer zeroed here) -> OIHW
         batched = self._wg_arena is not None and cp.name in self._wg_off
@@ -736,13 +752,16 @@ class Engine:
             if (self.h16 and H16_WGRAD and d16 is not None and cp.stride == 1 and cp.c_in_p % 8 == 0 and cp.c_in_p >= H16_MIN_K
                     and cp.c_out_p >= H16_MIN_K):
                 d.x = self._tma_src(x.t, cp.c_in_p, False)
-                d.dy = self._tma_src(d_pre, cp.c_out_p)
+                d.dy = self._tma_src(d16, cp.c_out_p)
                 if L.query("pmfb_wgrad16_ok", C.byref(d)) == 1:
-                    xb = torch.empty(x.t.shape, device=self.device, dtype=torch.bfloat16)
-                    L.call("pmfb_convert16", C.byref(_view(x.t)), n, h, w, cp.c_in_p, xb.data_ptr(), xb.stride(0), xb.stride(1),
-                           xb.stride(2), L.DT_BF16, self.st)
+                    xb = self._ensure_shadow(x, bf16=True)  # written by x's producer, else converted here once
+                    if xb is None:
+                        xb = torch.empty(x.t.shape, device=self.device, dtype=torch.bfloat16)
+                        L.call("pmfb_convert16", C.byref(_view(x.t)), n, h, w, cp.c_in_p, xb.data_ptr(), xb.stride(0),
+                               xb.stride(1), xb.stride(2), L.DT_BF16, self.st)
                     pairs = ((xb, d16),)
                     d.dtype = L.DT_BF16
+            assert pairs[0][1] is not None, "the fp32 output gradient was skipped for a layer whose wgrad needs it: " + cp.name
         for xa, dya in pairs:
             d.x = self._tma_src(xa, cp.c_in_p, cp.stride == 2)
             d.dy = self._tma_src(dya, cp.c_out_p)
@@ -821,8 +840,17 @@ class Engine:
             self.nbt_list.append(bn.nbt)
         return alpha, beta, mean, invstd
 
+    def _layer16(self, x, cp):
+        """True when BOTH backward kernels of this layer run from bf16 operands in "f16" mode (the fp32 copy of the
+        gradient with respect to the conv output is then never read and is not stored)."""
+        if not (self.h16 and H16_WGRAD and cp.stride == 1 and not cp.stem and cp.c_in_p % 8 == 0 and cp.c_out_p % 8 == 0
+                and cp.c_in_p >= H16_MIN_K and cp.c_out_p >= H16_MIN_K and x.shadow(True) is not None):
+            return False
+        reach = cp.dil * (cp.kh - 1) - cp.pad if cp.kh > 1 else 0
+        return max(abs(reach), abs(cp.pad)) <= 2  # taps inside the halo kernels' +-2 window
+
     def _bn_backward(self, bn, dy, a_t, stats, mul=None, z=None, act_z=ACT_NONE, leaky_x=0, want_colsum=False,
-                     g_out=None, g_acc=False):
+                     g_out=None, g_acc=False, need32=True):
         """Returns (d_pre [tf32-rounded gradient w.r.t. the conv output], colsum64 or None)."""
         alpha, beta, mean, invstd = stats
         n, h, w, c = a_t.shape
@@ -830,14 +858,17 @@ class Engine:
         dyv, mulv, zv, xv = _view(dy), (mul if isinstance(mul, View) else _view(mul)), _view(z), _view(a_t)
         L.call("pmfb_bn_bwd_reduce", C.byref(dyv), C.byref(mulv), C.byref(zv), act_z, C.byref(xv), mean.data_ptr(),
                invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), n, h, w, c, red.data_ptr(), self.st)
-        d_pre = torch.empty((n, h, w, c), device=self.device, dtype=torch.float32)
+        # "f16" mode: the same pass also stores d_pre as bf16, the operand of the kind::f16 dgrad / wgrad; the fp32 copy is
+        # skipped when nothing reads it (need32 False)
+        self._dpre16 = torch.empty((n, h, w, c), device=self.device, dtype=torch.bfloat16) if (self.h16 and c % 8 == 0 and c >= H16_MIN_K) else None
+        if self._dpre16 is None:
+            need32 = True
+        d_pre = torch.empty((n, h, w, c), device=self.device, dtype=torch.float32) if need32 else None
         cs = self.d64.take(c) if want_colsum else None
         gw, gb = self._pgrad(bn.name + ".weight", bn.weight), self._pgrad(bn.name + ".bias", bn.bias)
-        # "f16" mode: the same pass also stores d_pre as bf16, the operand of the kind::f16 dgrad
-        self._dpre16 = torch.empty((n, h, w, c), device=self.device, dtype=torch.bfloat16) if (self.h16 and c % 8 == 0 and c >= H16_MIN_K) else None
         L.call("pmfb_bn_bwd_apply16", C.byref(dyv), C.byref(mulv), C.byref(zv), act_z, C.byref(xv), mean.data_ptr(),
                invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), bn.weight.detach().data_ptr(), red.data_ptr(), leaky_x,
-               n, h, w, c, d_pre.data_ptr(), d_pre.stride(0), d_pre.stride(1), d_pre.stride(2), self.R, gw.data_ptr(),
+               n, h, w, c, _p(d_pre), c * h * w, c * w, c, self.R, gw.data_ptr(),
                gb.data_ptr(), _p(cs), _p(g_out), *( (g_out.stride(0), g_out.stride(1), g_out.stride(2)) if g_out is not None
                                                     else (0, 0, 0)), 1 if g_acc else 0, _p(self._dpre16), self.st)
         self.param_grads[bn.name + ".weight"] = gw
@@ -910,7 +941,7 @@ class Engine:
                 if shortcut is not None and shortcut.needs_grad:
                     g_out, g_acc = shortcut.grad_target()
                 d_pre, cs = self._bn_backward(bn, dy, a, stats, mul=mv, leaky_x=1, want_colsum=cp.bias is not None,
-                                              g_out=g_out, g_acc=g_acc)
+                                              g_out=g_out, g_acc=g_acc, need32=not self._layer16(x, cp))
                 if cs is not None:
                     self._bias_grad(cp, cs)
                 self._conv_bwd(x, cp, d_pre)
@@ -953,13 +984,14 @@ class Engine:
                         gp, acc = pcd.grad_target()  # d pcd = dy
                         self.pointwise(dy, gp, r1=gp if acc else None)
                     d_pre, cs = self._bn_backward(bn, dy, c_t, stats, mul=f.t, z=None, act_z=ACT_SIGMOID,
-                                                  want_colsum=cp.bias is not None)
+                                                  want_colsum=cp.bias is not None, need32=not self._layer16(x, cp))
                 else:
                     g_out, g_acc = (None, False)
                     if identity is not None and identity.needs_grad:
                         g_out, g_acc = identity.grad_target()
                     d_pre, cs = self._bn_backward(bn, dy, c_t, stats, mul=mv, z=y.t if post != ACT_NONE else None, act_z=post,
-                                                  want_colsum=cp.bias is not None, g_out=g_out, g_acc=g_acc)
+                                                  want_colsum=cp.bias is not None, g_out=g_out, g_acc=g_acc,
+                                                  need32=not self._layer16(x, cp))
                 if cs is not None:
                     self._bias_grad(cp, cs)
                 self._conv_bwd(x, cp, d_pre)
