@@ -549,10 +549,16 @@ def run_ours(args):
                    "sample": "%d frame(s)/step at %dx%d (the reference's PMFNet + loss classes, fp32, all host threads), fwd + trainer "
                              "loss block + bwd + optimizer step, 1 warm-up + 5 timed steps" % (args.cpu_sample_frames, H, W)}
     cfg = workload_config(B, H, W, world)
-    cfg["precision"] = "kind::tf32 operands, fp32 accumulate/storage"
+    from pmf_b200 import _lib as _PL
+    cfg["precision"] = {"f16": "kind::f16 UMMAs on 16-bit operand shadows (fp16 forward, bf16 dgrad/wgrad) for the >=64-channel "
+                               "stride-1 convolutions, kind::tf32 elsewhere; fp32 accumulate / storage / BatchNorm",
+                        "tf32": "kind::tf32 operands, fp32 accumulate/storage",
+                        "3xtf32": "3xTF32 hi/lo split operands (precise mode)"}[_PL.get_precision()]
+    cfg["precision_mode"] = _PL.get_precision()
     cfg["loss_impl"] = args.loss
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"f16": "f16/bf16+tf32 operands, f32 accumulate", "tf32": "tf32", "3xtf32": "3xtf32"}[_PL.get_precision()],
             "data": "synthetic", "config": cfg, "clocks": clocks,
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h_feat.numel() * 4 + h_label.numel() * 8, "d2h_bytes_per_step": 4},

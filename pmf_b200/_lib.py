@@ -162,16 +162,17 @@ def query(name, *args):
 
 
 # ---- precision mode of the tensor-core convolutions (process-wide; pmf_b200.precision(...) switches it)
-#   "tf32"   : kind::tf32 operands (rounded where they are produced), one UMMA per K step — the default, the arithmetic
-#              class of the reference's own GPU path (cuDNN with allow_tf32)
+#   "tf32"   : kind::tf32 operands (rounded where they are produced), one UMMA per K step — the arithmetic class of the
+#              reference's own GPU path (cuDNN with allow_tf32); what every eval-mode forward runs
 #   "3xtf32" : hi/lo operand split, three UMMAs per K step into the same TMEM accumulator (pmfb_split_tf32): fp32-class
 #              results, ~3x the tensor time; the parity mode for train-mode (batch-statistics) BatchNorm
-#   "f16"    : the stride-1 convolutions read 16-bit shadows of their operands (fp16 activations and weights in the forward
-#              pass — the same 10-bit mantissa as tf32 — and bf16 output gradients / weights in dgrad), kind::f16 UMMAs with
-#              fp32 accumulation: K = 16 channels per instruction instead of 8 at the same operand bytes; everything else
-#              (BatchNorm, elementwise, wgrad, storage) stays fp32
+#   "f16"    : THE DEFAULT.  In training passes the stride-1 convolutions with >= 64 channels read 16-bit shadows of
+#              their operands — fp16 activations and weights in the forward pass (the same 10-bit mantissa as tf32), bf16
+#              output gradients / weights / activations in dgrad and wgrad — through kind::f16 UMMAs with fp32 accumulation:
+#              K = 16 channels per instruction instead of 8 at the same operand bytes.  Everything else (BatchNorm,
+#              elementwise, thin layers, storage, eval-mode forwards) stays fp32 / tf32
 PRECISIONS = ("tf32", "3xtf32", "f16")
-_precision = os.environ.get("PMFB_PRECISION", "tf32").lower()
+_precision = os.environ.get("PMFB_PRECISION", "f16").lower()
 if _precision not in PRECISIONS:
     raise PmfbError("PMFB_PRECISION must be one of %s, got %r" % (PRECISIONS, _precision))
 

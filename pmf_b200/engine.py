@@ -844,7 +844,8 @@ class Engine:
         """True when BOTH backward kernels of this layer run from bf16 operands in "f16" mode (the fp32 copy of the
         gradient with respect to the conv output is then never read and is not stored)."""
         if not (self.h16 and H16_WGRAD and cp.stride == 1 and not cp.stem and cp.c_in_p % 8 == 0 and cp.c_out_p % 8 == 0
-                and cp.c_in_p >= H16_MIN_K and cp.c_out_p >= H16_MIN_K and x.shadow(True) is not None):
+                and cp.c_in_p >= H16_MIN_K and cp.c_out_p >= H16_MIN_K and x.shadow(True) is not None
+                and cp.c_in_p <= 512 and cp.c_out_p <= 512):  # the halo kernels stage <= 512 output channels
             return False
         reach = cp.dil * (cp.kh - 1) - cp.pad if cp.kh > 1 else 0
         return max(abs(reach), abs(cp.pad)) <= 2  # taps inside the halo kernels' +-2 window
