@@ -73,7 +73,7 @@ int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
 }
 
 int make_tmap_16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                 const uint32_t* box, bool bf16) {
+                 const uint32_t* box, bool bf16, bool swizzle64) {
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) return fail(PMFB_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available (no CUDA driver)");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(PMFB_ERR_INVALID, "tensor-map base %p not 16-byte aligned", ptr);
@@ -93,7 +93,8 @@ int make_tmap_16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* di
       return fail(PMFB_ERR_INVALID, "tensor-map stride[%d]=%llu not a multiple of 16 bytes", i, (unsigned long long)gstr[i]);
   }
   CUresult r = enc(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
-                   const_cast<void*>(ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   const_cast<void*>(ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PMFB_ERR_CUDA, "cuTensorMapEncodeTiled (16-bit) failed (%d) rank=%d", (int)r, rank);
   return PMFB_OK;

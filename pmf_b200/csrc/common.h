@@ -27,7 +27,7 @@ int make_tmap_f32(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
                   const uint64_t* strides_bytes, const uint32_t* box, bool swizzle32b_atom = false);
 // 16-bit (fp16 / bf16) tensor map, 128B swizzle, zero OOB fill: the K-major UMMA operands of the kind::f16 path.
 int make_tmap_16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                 const uint32_t* box, bool bf16);
+                 const uint32_t* box, bool bf16, bool swizzle64 = false);
 
 #define PMFB_CUDA_CHECK(expr)                                                            \
   do {                                                                                   \

@@ -43,6 +43,7 @@ struct HaloK {
   int nsb, a_bytes, a_box_bytes, nacc, tmem_cols, use_base_off, tma_store;
   int dtype, kslab;  // operand type (PMFB_DT_*) and channels per 128-byte slab (32 fp32 / 64 16-bit)
   int klast;         // 32-byte K steps of the LAST slab (a 32-channel layer fills half a 16-bit slab: 2 steps, not 4)
+  int row_bytes;     // operand row in shared memory: 128 (SWIZZLE_128B) or, for 16-bit layers of <= 32 channels, 64 (SWIZZLE_64B)
   float* out;
   long long o_sn, o_sy, o_sx;
   EpiParams epi;
@@ -82,11 +83,13 @@ __device__ __forceinline__ void mma_issue_loop(const HaloK& P, HCtrl* ctrl, uint
     const uint32_t idesc = F16 ? make_idesc_f16(128, (uint32_t)P.n_tile, P.dtype == PMFB_DT_BF16 ? 1u : 0u,
                                                 (P.dtype == PMFB_DT_BF16 || P.dtype == PMFB_DT_F16_BF16) ? 1u : 0u, 0, 0)
                                : make_idesc_tf32(128, (uint32_t)P.n_tile, 0, 0);
-    const uint32_t sbo = (uint32_t)pitch * 128u;
-    const uint32_t hi_a = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);   // bits 32..63 of the A descriptor
-    const uint32_t hi_b = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    const uint32_t rb = (uint32_t)P.row_bytes;
+    const uint32_t lay = rb == 128u ? (2u << 29) : (4u << 29);  // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
+    const uint32_t sbo = (uint32_t)pitch * rb;
+    const uint32_t hi_a = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | lay;   // bits 32..63 of the A descriptor
+    const uint32_t hi_b = (((8u * rb) >> 4) & 0x3FFFu) | (1u << 14) | lay;
     const uint32_t lbo_lo = (16u >> 4) << 16;
-    const uint32_t j_step = (uint32_t)(16 * pitch * 128) >> 4;
+    const uint32_t j_step = ((uint32_t)(16 * pitch) * rb) >> 4;
     uint32_t a_it = 0, b_it = 0, acc_it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++acc_it) {
       const uint32_t buf = acc_it % (uint32_t)P.nacc;
@@ -104,7 +107,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloK& P, HCtrl* ctrl, uint
           mbar_wait(&ctrl->full_b[st], (b_it / (uint32_t)P.nsb) & 1u);
           tc_fence_after();
           const uint32_t b_lo = ((smem_u32(b_buf + (size_t)st * b_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
-          uint32_t a_lo = a_lo0 + (uint32_t)((((P.tap_dh[t] + P.hy) * pitch + P.tap_dw[t] + P.hx) * 128) >> 4);
+          uint32_t a_lo = a_lo0 + (((uint32_t)((P.tap_dh[t] + P.hy) * pitch + P.tap_dw[t] + P.hx) * rb) >> 4);
           uint32_t d_col = d_base;
           if (s == P.ks - 1 && P.klast != 4) {  // partial last slab (e.g. 32 channels in a 64-channel 16-bit slab)
             for (int j = 0; j < P.mt; ++j) {
@@ -150,7 +153,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
   HCtrl* ctrl = reinterpret_cast<HCtrl*>(smem);
   uint8_t* a_buf = smem + kHCtrlBytes;
   uint8_t* b_buf = a_buf + 2 * (size_t)P.a_bytes;
-  const int b_bytes = P.n_tile * 128;
+  const int b_bytes = P.n_tile * P.row_bytes;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform -> uniform datapath
   const int lane = threadIdx.x & 31;
@@ -538,7 +541,10 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   HaloK P;
   P.n_taps = d->n_taps;
   P.dtype = d->dtype;
-  P.kslab = d->dtype == PMFB_DT_F32 ? 32 : 64;
+  // 16-bit layers with <= 32 input channels use 64-byte operand rows (SWIZZLE_64B): a 128-byte row would be half zero fill
+  const bool sw64 = d->dtype != PMFB_DT_F32 && d->c_in <= 32;
+  P.row_bytes = sw64 ? 64 : 128;
+  P.kslab = d->dtype == PMFB_DT_F32 ? 32 : (sw64 ? 32 : 64);
   if (d->dtype != PMFB_DT_F32 && d->c_in % 8) return fail(PMFB_ERR_INVALID, "conv halo: 16-bit operands need c_in %% 8 == 0 (c_in=%d)", d->c_in);
   P.ks = (d->c_in + P.kslab - 1) / P.kslab;
   {
@@ -584,8 +590,8 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
         const int nt = n_cands[ni];
         if (nt == 0 || mi * nt > 512) continue;
         // shared memory: two halo tiles + >= 2 weight stages + the epilogue staging tiles must fit
-        const int a_b = ((16 * mi + 2 * P.hy) * (8 + 2 * P.hx) * 128 + 1023) & ~1023;
-        const int nb_fit = (kHSmemBudget - kHCtrlBytes - 2 * a_b - kHEpiWarps * kHStageBytes) / (nt * 128);
+        const int a_b = ((16 * mi + 2 * P.hy) * (8 + 2 * P.hx) * P.row_bytes + 1023) & ~1023;
+        const int nb_fit = (kHSmemBudget - kHCtrlBytes - 2 * a_b - kHEpiWarps * kHStageBytes) / (nt * P.row_bytes);
         if (nb_fit < 2) continue;
         const long long items = (long long)P.tiles_x * ((d->out_h + 16 * mi - 1) / (16 * mi)) * d->n_batch * ((d->c_out + nt - 1) / nt);
         const long long waves = (items + sm_count - 1) / sm_count;
@@ -616,9 +622,9 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   P.nacc = (2 * mt * n_tile <= 512) ? 2 : 1;
   P.tmem_cols = pow2_cols_h(P.nacc * mt * n_tile);
   const int rows = 16 * mt + 2 * P.hy, pitch = 8 + 2 * P.hx;
-  P.a_box_bytes = rows * pitch * 128;
+  P.a_box_bytes = rows * pitch * P.row_bytes;
   P.a_bytes = (P.a_box_bytes + 1023) & ~1023;
-  const int b_bytes = n_tile * 128;
+  const int b_bytes = n_tile * P.row_bytes;
   static int tma_store_mode = -1;
   if (tma_store_mode < 0) {
     const char* e = getenv("PMFB_HALO_TMA_STORE");
@@ -645,7 +651,7 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   const bool h16 = d->dtype != PMFB_DT_F32;
   const uint64_t esz = h16 ? 2 : 4;
   uint32_t boxx[5] = {(uint32_t)P.kslab, (uint32_t)pitch, 1, (uint32_t)rows, 1};
-  rc = h16 ? make_tmap_16(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, boxx, d->dtype == PMFB_DT_BF16)
+  rc = h16 ? make_tmap_16(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, boxx, d->dtype == PMFB_DT_BF16, sw64)
            : make_tmap_f32(&tmx, d->x.ptr, 5, d->x.dims, d->x.strides, boxx);
   if (rc) return rc;
   int n_slabs = d->n_taps;
@@ -655,7 +661,7 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   uint64_t wdims[3] = {(uint64_t)d->c_in, (uint64_t)d->c_out, (uint64_t)n_slabs};
   uint64_t wstr[2] = {(uint64_t)d->c_in * esz, (uint64_t)d->c_in * d->c_out * esz};
   uint32_t boxw[3] = {(uint32_t)P.kslab, (uint32_t)n_tile, 1};
-  rc = h16 ? make_tmap_16(&tmw, d->w, 3, wdims, wstr, boxw, d->dtype != PMFB_DT_F16) : make_tmap_f32(&tmw, d->w, 3, wdims, wstr, boxw);
+  rc = h16 ? make_tmap_16(&tmw, d->w, 3, wdims, wstr, boxw, d->dtype != PMFB_DT_F16, sw64) : make_tmap_f32(&tmw, d->w, 3, wdims, wstr, boxw);
   if (rc) return rc;
 
   CUtensorMap tmo = tmw;  // placeholder when the direct-store path is used

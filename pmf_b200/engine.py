@@ -21,7 +21,8 @@ from . import _lib as L
 from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ConvDesc, Epilogue, TmaSrc, View, WeightJob, WgradDesc
 
 BN_EPS_DEFAULT = 1e-5
-H16_MIN_K = int(os.environ.get("PMFB_H16_MIN_K", "64"))
+H16_MIN_K = int(os.environ.get("PMFB_H16_MIN_K", "32"))      # forward / dgrad: 32 channels run on 64-byte operand rows
+H16_WGRAD_MIN = 64                                            # bf16 wgrad: one full 64-channel block per operand
 H16_WGRAD = os.environ.get("PMFB_H16_WGRAD", "1") != "0"
 N_SM = 148
 
@@ -468,7 +469,7 @@ class Engine:
         a = Act(torch.empty((n, h, w, c), device=self.device, dtype=torch.float32), needs_grad=needs_grad)
         if self.h16 and c % 8 == 0 and c >= H16_MIN_K:
             a.h = torch.empty((n, h, w, c), device=self.device, dtype=torch.float16)
-            if self.record and H16_WGRAD:
+            if self.record and H16_WGRAD and c >= H16_WGRAD_MIN:
                 a.hb = torch.empty((n, h, w, c), device=self.device, dtype=torch.bfloat16)
         return a
 
@@ -605,8 +606,7 @@ class Engine:
         d.o_sn, d.o_sy, d.o_sx = out_t.stride(0), out_t.stride(1), out_t.stride(2)
         d.epi = epi
         d.bn_stats = None
-        # 16-bit operands pay off from one full 64-channel slab on (a 32-channel layer would fill half of every 128-byte
-        # operand row with zeros: measured slower than the tf32 path)
+        # 16-bit operands from 32 channels on (32-channel layers use 64-byte operand rows; thinner ones stay tf32)
         if (x16 is not None and w16 is not None and not stride2 and c_in % 8 == 0 and c_in >= H16_MIN_K
                 and L.query("pmfb_conv16_ok", C.byref(d)) == 1):
             d.x = self._tma_src(x16, c_in, False)
@@ -749,8 +749,8 @@ class Engine:
         else:
             pairs = ((x.t, d_pre),)
             # "f16" mode: bf16 shadows of both operands (kind::f16, K = 16 pixels per UMMA) where the library takes them
-            if (self.h16 and H16_WGRAD and d16 is not None and cp.stride == 1 and cp.c_in_p % 8 == 0 and cp.c_in_p >= H16_MIN_K
-                    and cp.c_out_p >= H16_MIN_K):
+            if (self.h16 and H16_WGRAD and d16 is not None and cp.stride == 1 and cp.c_in_p % 8 == 0
+                    and cp.c_in_p >= H16_WGRAD_MIN and cp.c_out_p >= H16_WGRAD_MIN):
                 d.x = self._tma_src(x.t, cp.c_in_p, False)
                 d.dy = self._tma_src(d16, cp.c_out_p)
                 if L.query("pmfb_wgrad16_ok", C.byref(d)) == 1:
@@ -844,7 +844,7 @@ class Engine:
         """True when BOTH backward kernels of this layer run from bf16 operands in "f16" mode (the fp32 copy of the
         gradient with respect to the conv output is then never read and is not stored)."""
         if not (self.h16 and H16_WGRAD and cp.stride == 1 and not cp.stem and cp.c_in_p % 8 == 0 and cp.c_out_p % 8 == 0
-                and cp.c_in_p >= H16_MIN_K and cp.c_out_p >= H16_MIN_K and x.shadow(True) is not None
+                and cp.c_in_p >= H16_WGRAD_MIN and cp.c_out_p >= H16_WGRAD_MIN and x.shadow(True) is not None
                 and cp.c_in_p <= 512 and cp.c_out_p <= 512):  # the halo kernels stage <= 512 output channels
             return False
         reach = cp.dil * (cp.kh - 1) - cp.pad if cp.kh > 1 else 0
