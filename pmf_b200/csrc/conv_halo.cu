@@ -548,7 +548,7 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   if (d->dtype != PMFB_DT_F32 && d->c_in % 8) return fail(PMFB_ERR_INVALID, "conv halo: 16-bit operands need c_in %% 8 == 0 (c_in=%d)", d->c_in);
   P.ks = (d->c_in + P.kslab - 1) / P.kslab;
   {
-    const int per_step = P.kslab / 4;  // channels per 32-byte K step
+    const int per_step = d->dtype == PMFB_DT_F32 ? 8 : 16;  // channels per 32-byte K step
     const int rem = d->c_in - (P.ks - 1) * P.kslab;
     P.klast = (rem + per_step - 1) / per_step;
   }

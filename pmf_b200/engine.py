@@ -21,7 +21,10 @@ from . import _lib as L
 from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ConvDesc, Epilogue, TmaSrc, View, WeightJob, WgradDesc
 
 BN_EPS_DEFAULT = 1e-5
-H16_MIN_K = int(os.environ.get("PMFB_H16_MIN_K", "32"))      # forward / dgrad: 32 channels run on 64-byte operand rows
+# forward / dgrad: 16-bit operands from one full 64-channel slab on.  (32-channel layers CAN run on 64-byte operand rows,
+# SWIZZLE_64B, with PMFB_H16_MIN_K=32 -- parity-green but measured slower than their tf32 path: 0.30 vs 0.24 ms for the
+# full-resolution 32->32 3x3 layers, which are not MMA-bound.)
+H16_MIN_K = int(os.environ.get("PMFB_H16_MIN_K", "64"))
 H16_WGRAD_MIN = 64                                            # bf16 wgrad: one full 64-channel block per operand
 H16_WGRAD = os.environ.get("PMFB_H16_WGRAD", "1") != "0"
 N_SM = 148
@@ -606,7 +609,7 @@ class Engine:
         d.o_sn, d.o_sy, d.o_sx = out_t.stride(0), out_t.stride(1), out_t.stride(2)
         d.epi = epi
         d.bn_stats = None
-        # 16-bit operands from 32 channels on (32-channel layers use 64-byte operand rows; thinner ones stay tf32)
+        # 16-bit operands from H16_MIN_K channels on (thinner layers stay on the tf32 path)
         if (x16 is not None and w16 is not None and not stride2 and c_in % 8 == 0 and c_in >= H16_MIN_K
                 and L.query("pmfb_conv16_ok", C.byref(d)) == 1):
             d.x = self._tma_src(x16, c_in, False)
