@@ -389,6 +389,10 @@ int pmfb_lut_remap(const int64_t* labels, int64_t n, const int32_t* lut, int32_t
 int pmfb_merge_cameras(const int64_t* point_idx, const float* conf, const int64_t* argmax, const int32_t* cam,
                        int64_t n_entries, int64_t pc_size, uint64_t* scratch, int64_t* merged, void* stream);
 
+/* IOUEval.addBatch (pc_processor/metrics/iou_eval.py:31-57) on the device: conf[pred[i], target[i]] += 1 (row = prediction,
+ * column = ground truth; int64 nclasses x nclasses matrix, accumulated; entries outside [0, nclasses) are skipped). */
+int pmfb_confusion_add(const int64_t* pred, const int64_t* target, int64_t n, int32_t nclasses, int64_t* conf, void* stream);
+
 /* Perspective projection + scatter (parser.py:209-227, perspective_view_loader.py:87-131):
  * q = M*[x y z 1]^T in float64, keep x>0.5 and 0<u<W, 0<v<H, truncate to (row,col); per pixel the point
  * with the HIGHEST index wins (numpy fancy-assignment order).  Two passes over `winner` (int32 H*W,

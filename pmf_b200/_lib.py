@@ -103,6 +103,7 @@ _SIGNATURES = {
     "pmfb_argmax_nchw": ([vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp], C.c_int),
     "pmfb_lut_remap": ([vp, i64, vp, i32, vp, vp], C.c_int),
     "pmfb_merge_cameras": ([vp, vp, vp, vp, i64, i64, vp, vp, vp], C.c_int),
+    "pmfb_confusion_add": ([vp, vp, i64, i32, vp, vp], C.c_int),
     "pmfb_project_scatter": ([vp, vp, i64, C.POINTER(C.c_double), i32, i32, vp, vp, vp, vp, vp, vp, vp, vp], C.c_int),
 }
 

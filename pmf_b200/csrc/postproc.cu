@@ -277,6 +277,25 @@ __global__ void merge_cameras_pass2(const unsigned long long* __restrict__ best,
   }
 }
 
+// ---------------------------------------------------------------------------------------------- confusion matrix
+// IOUEval.addBatch (pc_processor/metrics/iou_eval.py:31-57): conf[pred, target] += 1 for every pixel.  Per-block histogram
+// in shared memory (c*c <= 4096 counters), one global atomic per touched cell and block.
+__global__ void __launch_bounds__(256)
+confusion_add_kernel(const long long* __restrict__ pred, const long long* __restrict__ target, long long n, int c,
+                     unsigned long long* __restrict__ conf) {
+  extern __shared__ unsigned int s_conf[];
+  const int cc = c * c;
+  for (int i = threadIdx.x; i < cc; i += blockDim.x) s_conf[i] = 0;
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = pred[i], t = target[i];
+    if (p >= 0 && p < c && t >= 0 && t < c) atomicAdd(&s_conf[(int)p * c + (int)t], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cc; i += blockDim.x)
+    if (s_conf[i]) atomicAdd(conf + i, (unsigned long long)s_conf[i]);
+}
+
 // ---------------------------------------------------------------------------------------------- projection
 __global__ void fill_i32_kernel(int* p, long long n, int v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
@@ -443,6 +462,20 @@ extern "C" int pmfb_merge_cameras(const int64_t* point_idx, const float* conf, c
                                               reinterpret_cast<const long long*>(argmax), pc_size,
                                               reinterpret_cast<long long*>(merged));
   PMFB_LAUNCH_CHECK("merge_cameras_pass2");
+  return PMFB_OK;
+}
+
+extern "C" int pmfb_confusion_add(const int64_t* pred, const int64_t* target, int64_t n, int32_t nclasses, int64_t* conf,
+                                  void* stream) {
+  REQ(nclasses >= 1 && nclasses <= 64 && conf && n >= 0, "confusion_add: bad arguments (nclasses <= 64)");
+  if (n == 0) return PMFB_OK;
+  REQ(pred && target, "confusion_add: null inputs");
+  long long b = (n + 255) / 256;
+  if (b > 148 * 4) b = 148 * 4;
+  confusion_add_kernel<<<(int)b, 256, (size_t)nclasses * nclasses * 4, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(pred), reinterpret_cast<const long long*>(target), n, nclasses,
+      reinterpret_cast<unsigned long long*>(conf));
+  PMFB_LAUNCH_CHECK("confusion_add_kernel");
   return PMFB_OK;
 }
 

@@ -256,6 +256,11 @@ class WeightCache:
         self.precise = False  # set by the Engine of the pass (pmf_b200._lib precision mode)
         self.h16 = False      # "f16" mode: fp16 forward / bf16 dgrad copies of the packed weights
         self.arenas = None
+        # frozen (pmf_b200.export / PMFNet.freeze): inference with fixed parameters — weights are packed once and the
+        # eval-mode BatchNorm affines (gamma * invstd, beta - mean * gamma * invstd) folded once, kept here, and no pass
+        # re-derives them (a captured eval graph then holds the convolutions and their fused epilogues only)
+        self.frozen = False
+        self.folded = {}
 
     @staticmethod
     def _convert16(src, dst, dt, stream):
@@ -337,6 +342,8 @@ class WeightCache:
         w = cp.weight
         key = cp.name
         e = self.entries.get(key)
+        if self.frozen and e is not None and e.get("fwd") is not None and not need_dgrad:
+            return e
         if self.always:
             tag = ("epoch", self.epoch)
             if e is not None and e["tag"] == tag and (e["dgrad"] is not None or not need_dgrad):
@@ -813,7 +820,14 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------ BatchNorm pieces
     def _bn_eval_affine(self, bn):
-        ab = self.f32.take(2 * bn.c)
+        if self.cache.frozen:
+            hit = self.cache.folded.get(bn.name)
+            if hit is not None:
+                return hit
+            ab = torch.empty(2 * bn.c, device=self.device, dtype=torch.float32)
+            self.cache.folded[bn.name] = (ab[:bn.c], ab[bn.c:])
+        else:
+            ab = self.f32.take(2 * bn.c)
         alpha, beta = ab[:bn.c], ab[bn.c:]
         L.call("pmfb_bn_finalize", None, 0, bn.c, _p(bn.weight.detach()), _p(bn.bias.detach()), bn.running_mean.data_ptr(),
                bn.running_var.data_ptr(), bn.momentum, bn.eps, alpha.data_ptr(), beta.data_ptr(), None, None, self.st)
@@ -966,9 +980,15 @@ class Engine:
         if not self.train:
             alpha, beta = self._bn_eval_affine(bn)
             if e["bias"] is not None:  # beta' = alpha*bias + beta  (tiny per-channel vector op on the device)
-                b2 = self.f32.take(bn.c)
-                self.pointwise(e["bias"].view(1, 1, 1, -1), b2.view(1, 1, 1, -1), alpha1=alpha, beta1=beta)
-                beta = b2
+                hit = self.cache.folded.get(bn.name + "|bias") if self.cache.frozen else None
+                if hit is not None:
+                    beta = hit
+                else:
+                    b2 = torch.empty(bn.c, device=self.device, dtype=torch.float32) if self.cache.frozen else self.f32.take(bn.c)
+                    self.pointwise(e["bias"].view(1, 1, 1, -1), b2.view(1, 1, 1, -1), alpha1=alpha, beta1=beta)
+                    if self.cache.frozen:
+                        self.cache.folded[bn.name + "|bias"] = b2
+                    beta = b2
             self._conv_fwd(x, cp, y.t, self._epi(alpha1=alpha, beta1=beta, r1=id_t, act=post, mul=f_t, r2=pcd_t,
                                                  rnd=1 if rnd else 0))
             return y

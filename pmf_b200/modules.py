@@ -302,7 +302,10 @@ class _GraphedPMF:
         self.dev = pcd.device
         n, c_pcd, h, w = pcd.shape
         self.shape = (n, c_pcd, h, w)
-        self.cache = WeightCache(always=True)
+        frozen = bool(getattr(mod, "_frozen", False)) and not record and not mod.training
+        # frozen inference: the eager pass that preceded this capture packed the weights and folded the BatchNorm affines
+        # into mod._cache; the captured graph re-uses them and contains no packing / finalisation kernels
+        self.cache = mod._cache if frozen else WeightCache(always=True)
         self.cache.precise = _L.get_precision() == "3xtf32"
         self.cache.h16 = _L.get_precision() == "f16" and mod.training
         self.E = None
@@ -317,7 +320,8 @@ class _GraphedPMF:
         self.img7 = self.E_in.new(n, h, w, 32, needs_grad=False)
         self.pcd = self.E_in.new(n, h, w, (c_pcd + 3) // 4 * 4, needs_grad=False)
         self._stage_inputs(pcd, img)
-        self.cache.build_table(G.ModuleParams(mod), record, self.dev)  # every weight packed by one launch per pass
+        if not frozen:
+            self.cache.build_table(G.ModuleParams(mod), record, self.dev)  # every weight packed by one launch per pass
         torch.cuda.synchronize(self.dev)
         l0 = _L.launches
         with torch.cuda.graph(self.g_fwd, pool=self.pool, capture_error_mode="thread_local"):  # NCCL watchdog threads may poll events
@@ -482,6 +486,19 @@ class PMFNet(nn.Module):
         self._graphs = {}
         self._seen = set()
 
+    def freeze(self, frozen=True):
+        """Inference with FIXED parameters: from the next eval forward on, the conv weights are packed
+        once and the eval-mode BatchNorm layers folded once into per-channel epilogue vectors — conv -> BN -> ReLU folds in
+        front of the activation, the SalsaNext / fusion order conv -> LeakyReLU -> BN behind it — and every later forward
+        (CUDA-graph replay) runs the convolutions with their fused epilogues only.  Later changes to the parameters are
+        NOT seen until ``freeze(False)`` / ``freeze()`` is called again.  See pmf_b200.export for the on-disk form."""
+        self._frozen = bool(frozen)
+        self._cache = WeightCache()
+        self._cache.frozen = self._frozen
+        self._graphs.clear()
+        self._seen.clear()
+        return self
+
     def _dropout_masks(self):
         if self._dropout_override is not None:
             return self._dropout_override
@@ -503,7 +520,7 @@ class PMFNet(nn.Module):
         drop = tuple((n, m.training, m.p) for n, m in self.named_modules() if isinstance(m, nn.Dropout2d))
         ptrs = tuple(p.data_ptr() for p in params) + tuple(b.data_ptr() for b in self.buffers())
         return (tuple(pcd.shape), tuple(img.shape), str(pcd.device), self.training, record, drop, ptrs,
-                tuple(p.requires_grad for p in params), _L.get_precision())
+                tuple(p.requires_grad for p in params), _L.get_precision(), bool(getattr(self, "_frozen", False)))
 
     def forward(self, pcd_feature, img_feature):
         _require_cuda(pcd_feature, img_feature)
