@@ -43,6 +43,8 @@ def parse():
                     help="our arm: pmf_b200.loss.TrainerLoss implementation (fused = libpmf_b200.so; torch = the block as the "
                          "unchanged trainer.py runs it)")
     ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
+    ap.add_argument("--backbone", default="resnet34", help="camera encoder (BASELINE config 4: resnet50)")
+    ap.add_argument("--nclasses", type=int, default=20, help="20 SemanticKITTI / 17 nuScenes")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
@@ -60,10 +62,13 @@ def make_frames(B, H, W, seed):
     """(B,8,H,W) normalised frame tensor + (B,H,W) labels, as tasks/pmf/trainer.py:291-299 hands them to the model."""
     from tests import synth
     feat, _mask, label = synth.frame_tensor(B, H, W, seed=seed, density=0.1)
+    if NCLASSES < 20:
+        label = label % NCLASSES  # nuScenes-shaped: 16 classes + ignored 0
     return feat, label
 
 
 NCLASSES, LAMBDA, GAMMA, TAU = 20, 1.0, 0.5, 0.7  # tasks/pmf/config_server_kitti.yaml:29-31
+BACKBONE = "resnet34"
 
 
 def load_reference():
@@ -198,7 +203,7 @@ class _RefStepper:
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 self.model = self.ref.models.PMFNet(pcd_channels=5, img_channels=3, nclasses=NCLASSES, base_channels=32,
-                                                    image_backbone="resnet34", imagenet_pretrained=False).to(self.dev)
+                                                    image_backbone=BACKBONE, imagenet_pretrained=False).to(self.dev)
             if channels_last:
                 self.model = self.model.to(memory_format=torch.channels_last)
             self.model.train()
@@ -209,7 +214,7 @@ class _RefStepper:
             from oracle import pmf_oracle as po
             self.kind = "port"
             self.po = po
-            sd = po.synth_state_dict(po.pmf_param_shapes(NCLASSES, 32, "resnet34"), seed=1)
+            sd = po.synth_state_dict(po.pmf_param_shapes(NCLASSES, 32, BACKBONE), seed=1)
             self.params = {k: (v.clone().to(self.dev).requires_grad_(True) if v.dtype.is_floating_point and "running" not in k
                                else v.clone().to(self.dev)) for k, v in sd.items()}
             self.loss = oracle_loss_block
@@ -226,7 +231,7 @@ class _RefStepper:
             if self.kind == "reference":
                 lid, cam = self.model(pcd, img)
             else:
-                lid, cam, ctx = self.po.pmf_forward(self.params, pcd, img, "resnet34", train=True, return_ctx=True)
+                lid, cam, ctx = self.po.pmf_forward(self.params, pcd, img, BACKBONE, train=True, return_ctx=True)
         loss = self.loss(lid.float(), cam.float(), label)
         self.opt_a.zero_grad(set_to_none=True)
         self.opt_b.zero_grad(set_to_none=True)
@@ -258,9 +263,10 @@ def cpu_reference_step_rate(B, H, W, steps, warmup, threads=None):
 
 def workload_config(B, H, W, world):
     px = H * W
-    return {"workload": "PMF-ResNet34 SemanticKITTI-shaped synthetic, batch %d/GPU, %dx%d camera grid, fwd + trainer loss block "
+    return {"workload": "PMF-%s %s-shaped synthetic, batch %d/GPU, %dx%d camera grid, fwd + trainer loss block "
                         "(focal + Lovasz on both heads + perception-aware KL) + bwd + AdamW/SGD step, train-mode BN + Dropout2d"
-                        % (B, H, W),
+                        % (BACKBONE.replace("resnet", "ResNet"), "SemanticKITTI" if NCLASSES == 20 else "nuScenes", B, H, W),
+            "backbone": BACKBONE, "nclasses": NCLASSES,
             "frames_per_gpu": B, "height": H, "width": W, "parallelism": "dp%d (frame-parallel, gradient all-reduce over NCCL)" % world,
             "l2": "no explicit flush: per-step working set (>20 GB of activations) >> 126 MB L2",
             "step_gflop_per_frame": STEP_KFLOP_PER_PX * px / 1e6}
@@ -330,7 +336,7 @@ def gpu_eager_subprocess(B, H, W, steps=4, warmup=2, timeout=600):
     """Runs run_gpu_eager in a fresh process (its ~100 GB of eager activations must not share the allocator with our CUDA
     graphs) and returns the parsed object; on failure {"error": ...}."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "gpu-eager", "--batch", str(B), "--height", str(H), "--width", str(W),
-           "--steps", str(steps), "--warmup", str(warmup)]
+           "--steps", str(steps), "--warmup", str(warmup), "--backbone", BACKBONE, "--nclasses", str(NCLASSES)]
     env = dict(os.environ)
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
@@ -378,7 +384,7 @@ def run_ours(args):
     B, H, W = args.batch, args.height, args.width
 
     torch.manual_seed(1)
-    model = pmf_b200.PMFNet(5, 3, 20, 32, False, "resnet34").to(dev)
+    model = pmf_b200.PMFNet(5, 3, NCLASSES, 32, False, BACKBONE).to(dev)
     model.train()
     net = model
     if world > 1:
@@ -867,7 +873,14 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
 
 
 def main():
+    global NCLASSES, BACKBONE, METRIC, FWD_KFLOP_PER_PX, STEP_KFLOP_PER_PX
     args = parse()
+    NCLASSES, BACKBONE = args.nclasses, args.backbone
+    if args.backbone == "resnet50":  # PMF-ResNet50 forward 2156.8 kFLOP/px, forward + backward ~6450
+        FWD_KFLOP_PER_PX, STEP_KFLOP_PER_PX = 2156.8, 6450.0
+    if (args.backbone, args.batch, args.height, args.width) != ("resnet34", 8, 480, 640):
+        METRIC = "frames/sec PMF-%s fwd+bwd (%dx%d camera grid, batch %d/GPU)" % (
+            args.backbone.replace("resnet", "ResNet"), args.height, args.width, args.batch)
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "gpu-eager":
