@@ -22,4 +22,9 @@ def test_frame_parallel_equals_torch_ddp_two_ranks():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "fp_worker.py")],
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        open(os.path.join(ROOT, "gpurun_out", "frame_parallel.log"), "w").write(r.stdout + "\n" + r.stderr)
+    except OSError:
+        pass
     assert r.returncode == 0 and "frame parallel ok" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
