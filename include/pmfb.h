@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PMFB_ABI_VERSION 4
+#define PMFB_ABI_VERSION 5
 #define PMFB_MAX_TAPS 9
 
 typedef enum {
@@ -105,7 +105,11 @@ typedef struct {
   /* PMFB_DT_*: element type of x.ptr and w (x.strides stay in BYTES).  16-bit operands: stride-1 layers on the halo kernel
    * only (pmfb_conv16_ok), c_in % 8 == 0. */
   int32_t dtype;
-  int32_t reserved;
+  /* 1: `out` addresses an fp16 buffer (o_sn / o_sy / o_sx stay ELEMENT strides, c_out and o_sx multiples of 8): the result
+   * is stored rounded to fp16 and the fused statistics are those of the stored values.  Only with the fused-statistics
+   * epilogue of the halo kernel (training-mode conv -> [LeakyReLU] -> BatchNorm: the pre-BN activation is read twice more by
+   * the BatchNorm passes and never by a convolution). */
+  int32_t out_half;
 } pmfb_conv_desc;
 
 /* Weight gradient on tcgen05: dw[tap][ci][co] += sum_{n,y,x} x[n,y+dh,x+dw,..,dc+ci] * dy[n,y,x,co]
@@ -199,10 +203,12 @@ int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, 
 /* pmfb_pointwise that ALSO stores the result as 16-bit shadows (same element strides and channel offset as out): out16 in
  * dtype16 = PMFB_DT_F16 or PMFB_DT_BF16 (fp16 values saturate to the fp16 range) and / or out16_bf16 in bf16.  The BN-apply
  * pass that produces a conv input writes the operands the kind::f16 convolution (fp16) and weight gradient (bf16) will read
- * in the same pass.  Both NULL: identical to pmfb_pointwise. */
+ * in the same pass.  Both NULL: identical to pmfb_pointwise.
+ * in_half: the input view addresses an fp16 buffer (the pre-BatchNorm activation a convolution stored with
+ * pmfb_conv_desc.out_half) with the given ELEMENT strides. */
 int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n, int32_t h,
                      int32_t w, int32_t c, const pmfb_epilogue* epi, void* out16, int32_t dtype16, void* out16_bf16,
-                     void* stream);
+                     int32_t in_half, void* stream);
 
 /* 16-bit shadow of an fp32 NHWC view (c % 8 == 0; out16 has element strides o_sn / o_sy / o_sx, channel stride 1). */
 int pmfb_convert16(const pmfb_view* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out16, int64_t o_sn, int64_t o_sy,
@@ -250,7 +256,11 @@ int pmfb_bn_bwd_apply16(const pmfb_view* dy, const pmfb_view* mul, const pmfb_vi
                         const float* beta, const float* gamma, const double* red, int32_t leaky_x, int32_t n,
                         int32_t h, int32_t w, int32_t c, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
                         int32_t round_out, float* dgamma, float* dbeta, double* colsum, float* g_out, int64_t g_sn,
-                        int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* dx16, void* stream);
+                        int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* dx16, int32_t x_half, void* stream);
+/* x_half (here and in pmfb_bn_bwd_apply16): the view x addresses an fp16 buffer (element strides), see pmfb_conv_desc.out_half. */
+int pmfb_bn_bwd_reduce16(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z, const pmfb_view* x,
+                         const float* mean, const float* invstd, const float* alpha, const float* beta, int32_t n, int32_t h,
+                         int32_t w, int32_t c, double* red, int32_t x_half, void* stream);
 
 /* out[i*C + c] (+)= sum over pixels (per image if per_image) of x; double accumulators, caller zeroes. */
 int pmfb_colsum(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t per_image, double* out,

@@ -32,30 +32,52 @@ def round_tf32(x):
     return x + (r - x).detach()
 
 
+def round_half(x):
+    """Round to fp16 (saturating) as a differentiable straight-through op: EMULATION of the "f16" mode's fp16 storage of
+    the pre-BatchNorm activation (pmfb_conv_desc.out_half)."""
+    with torch.no_grad():
+        r = x.detach().clamp(-65504.0, 65504.0).half().float()
+    return x + (r - x).detach()
+
+
 class Ctx:
     """tf32=False (default): the reference's fp32 arithmetic (this is what is pinned to the reference).
     tf32=True: conv operands (input and weight) are rounded to tf32 before every convolution, accumulation stays
     fp32 — an emulation of the tcgen05 kind::tf32 path that lets tests separate indexing bugs (O(1) errors) from
-    the expected operand-rounding noise."""
+    the expected operand-rounding noise.
+    half_pre_bn=True (train mode only): the input of a training-mode BatchNorm that directly follows a convolution the
+    engine's "f16" mode stores in fp16 (stride 1, taps inside the halo kernel's window, c_out a multiple of 8 and <= 256)
+    is rounded to fp16 first — the batch statistics, the normalisation and both backward passes then see the rounded
+    values, as on the device."""
 
-    def __init__(self, sd, train=False, dropout=None, tf32=False):
+    def __init__(self, sd, train=False, dropout=None, tf32=False, half_pre_bn=False):
         self.sd = sd
         self.train = train
         self.dropout = dropout or {}
         self.new_stats = {}
         self.tf32 = tf32
+        self.half_pre_bn = half_pre_bn
+        self._half_geom = False  # the engine would store the last convolution's (activated) output as fp16
 
     def conv(self, x, name, stride=1, padding=0, dilation=1):
         w = self.sd[name + ".weight"]
         if self.tf32:
             x, w = round_tf32(x), round_tf32(w)
-        return F.conv2d(x, w, self.sd.get(name + ".bias"), stride=stride, padding=padding, dilation=dilation)
+        y = F.conv2d(x, w, self.sd.get(name + ".bias"), stride=stride, padding=padding, dilation=dilation)
+        if self.half_pre_bn and self.train:
+            k = w.shape[2]
+            reach = max(padding, dilation * (k - 1) - padding) if k > 1 else 0
+            self._half_geom = (stride == 1 and w.shape[0] % 8 == 0 and w.shape[0] <= 256 and (reach <= 2 or k == 7))
+        return y
 
     def bn(self, x, name):
         w, b = self.sd[name + ".weight"], self.sd[name + ".bias"]
         rm, rv = self.sd[name + ".running_mean"], self.sd[name + ".running_var"]
         if not self.train:
             return F.batch_norm(x, rm, rv, w, b, False, BN_MOMENTUM, BN_EPS)
+        if self.half_pre_bn and getattr(self, "_half_geom", False):
+            x = round_half(x)
+        self._half_geom = False
         rm2, rv2 = rm.detach().clone(), rv.detach().clone()
         y = F.batch_norm(x, rm2, rv2, w, b, True, BN_MOMENTUM, BN_EPS)
         self.new_stats[name + ".running_mean"] = rm2

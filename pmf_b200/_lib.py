@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmf_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_TAPS = 9
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
@@ -37,7 +37,7 @@ class ConvDesc(C.Structure):
                 ("tap_dh", i32 * MAX_TAPS), ("tap_wi", i32 * MAX_TAPS), ("use_tap_wi", i32), ("n_batch", i32),
                 ("out_h", i32), ("out_w", i32), ("tile_w", i32),
                 ("tile_h", i32), ("n_tile", i32), ("out", C.c_void_p), ("o_sn", i64), ("o_sy", i64), ("o_sx", i64),
-                ("epi", Epilogue), ("bn_stats", C.c_void_p), ("dtype", i32), ("reserved", i32)]
+                ("epi", Epilogue), ("bn_stats", C.c_void_p), ("dtype", i32), ("out_half", i32)]
 
 
 class WgradDesc(C.Structure):
@@ -65,10 +65,11 @@ _SIGNATURES = {
     "pmfb_conv_wgrad": ([C.POINTER(WgradDesc), vp], C.c_int),
     "pmfb_conv16_ok": ([C.POINTER(ConvDesc)], C.c_int),
     "pmfb_wgrad16_ok": ([C.POINTER(WgradDesc)], C.c_int),
-    "pmfb_pointwise16": ([VP, vp, i64, i64, i64, i32, i32, i32, i32, C.POINTER(Epilogue), vp, i32, vp, vp], C.c_int),
+    "pmfb_pointwise16": ([VP, vp, i64, i64, i64, i32, i32, i32, i32, C.POINTER(Epilogue), vp, i32, vp, i32, vp], C.c_int),
+    "pmfb_bn_bwd_reduce16": ([VP, VP, VP, i32, VP, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, vp], C.c_int),
     "pmfb_convert16": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
     "pmfb_bn_bwd_apply16": ([VP, VP, VP, i32, VP, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i64, i64, i64,
-                             i32, vp, vp, vp, vp, i64, i64, i64, i32, vp, vp], C.c_int),
+                             i32, vp, vp, vp, vp, i64, i64, i64, i32, vp, i32, vp], C.c_int),
     "pmfb_memset_zero": ([vp, C.c_size_t, vp], C.c_int),
     "pmfb_pack_input": ([vp, i64, i64, i64, i64, i32, i32, i32, i32, i32, vp, i32, i64, i32, vp], C.c_int),
     "pmfb_nhwc_to_nchw": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.h"
 #include "epilogue.cuh"
@@ -31,6 +32,13 @@ __device__ __forceinline__ const float* pv_at(const PV& v, unsigned pix, unsigne
   if (v.linear) return v.p + (long long)pix * v.sx + c;
   const unsigned n = pix / hw, q = pix - n * hw, y = q / w, x = q - y * w;
   return v.p + (long long)n * v.sn + (long long)y * v.sy + (long long)x * v.sx + c;
+}
+
+// LIN: the view is known (checked on the host) to be pixel-linear: no runtime branch, no divisions in the unrolled loops
+template <bool LIN>
+__device__ __forceinline__ const float* pv_at_t(const PV& v, unsigned pix, unsigned hw, unsigned w, int c) {
+  if constexpr (LIN) return v.p + (long long)pix * v.sx + c;
+  else return pv_at(v, pix, hw, w, c);
 }
 
 static inline PV pv(const pmfb_view* v, int h, int w) {
@@ -169,7 +177,16 @@ __device__ __forceinline__ float act_grad(int act, float z) {
 // g = dy * mul * act'(z); z is either stored (zv) or recomputed as act(alpha*x + beta) (sigmoid gate).
 // MUL / ZST (stored z) are compile-time: a launch without them (the plain conv -> LeakyReLU -> BN backward, most of the
 // bytes) carries two operand streams, keeps four pixels of loads in flight per thread and has no dead registers.
-template <bool MUL, bool ZST>
+// four packed fp16 values (8 bytes) -> float4
+__device__ __forceinline__ float4 unpack_h4(uint2 r) {
+  const __half2 a = *reinterpret_cast<const __half2*>(&r.x), b = *reinterpret_cast<const __half2*>(&r.y);
+  const float2 fa = __half22float2(a), fb = __half22float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+// XH: x (the stored pre-BatchNorm activation) is an fp16 buffer with the same ELEMENT strides; its four values travel
+// packed (8 bytes) until they are used, and the kernels keep twice as many pixels in flight (same bytes in flight per thread).
+template <bool MUL, bool ZST, bool XH>
 struct GradIn {
   PV dy, mul, z, x;
   const float* mean;
@@ -177,36 +194,50 @@ struct GradIn {
   const float* alpha;
   const float* beta;
   int act_z;
-  struct Loaded { float4 g, xv, m[MUL ? 1 : 0], zz[ZST ? 1 : 0]; };
-  struct Consts { float4 mu, is, a, b; };
+  struct Loaded { float4 g, xv[XH ? 0 : 1], m[MUL ? 1 : 0], zz[ZST ? 1 : 0]; uint2 xh[XH ? 1 : 0]; };
+  // XH launches always carry BatchNorm statistics (host-checked) and recompute z = act(alpha*x + beta) only in the gated
+  // (MUL) form: the plain conv -> LeakyReLU -> BN backward then keeps 8 fewer constant registers per thread.
+  static constexpr bool kRecomp = !ZST && (MUL || !XH);
+  struct Consts { float4 mu, is, a[kRecomp ? 1 : 0], b[kRecomp ? 1 : 0]; };
+  __device__ __forceinline__ bool has_bn() const { return XH || mean != nullptr; }
   __device__ __forceinline__ void prep(int c, Consts& k) const {
-    k.mu = k.is = k.a = k.b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mean) { k.mu = ld4(mean + c); k.is = ld4(invstd + c); }
-    if (!ZST && act_z) { k.a = ld4(alpha + c); k.b = ld4(beta + c); }
+    k.mu = k.is = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_bn()) { k.mu = ld4(mean + c); k.is = ld4(invstd + c); }
+    if constexpr (kRecomp) {
+      k.a[0] = k.b[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act_z) { k.a[0] = ld4(alpha + c); k.b[0] = ld4(beta + c); }
+    }
   }
   __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const {
-    l.g = ld4(pv_at(dy, pix, hw, w, c));
+    l.g = ld4(pv_at_t<XH>(dy, pix, hw, w, c));
     if constexpr (MUL) l.m[0] = ld4(pv_at(mul, pix, hw, w, c));
-    if (x.p) l.xv = ld4(pv_at(x, pix, hw, w, c));
-    if constexpr (ZST) l.zz[0] = ld4(pv_at(z, pix, hw, w, c));
+    if constexpr (XH) {  // x present and pixel-linear (host-checked)
+      l.xh[0] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(x.p) + ((long long)pix * x.sx + c)));
+    } else {
+      if (x.p) l.xv[0] = ld4(pv_at(x, pix, hw, w, c));
+    }
+    if constexpr (ZST) l.zz[0] = ld4(pv_at_t<XH>(z, pix, hw, w, c));
   }
   __device__ __forceinline__ void finish(const Consts& k, const Loaded& l, float4& g, float4& xhat, float4& xv) const {
     g = l.g;
     if constexpr (MUL) { g.x *= l.m[0].x; g.y *= l.m[0].y; g.z *= l.m[0].z; g.w *= l.m[0].w; }
-    xv = x.p ? l.xv : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act_z) {
-      float4 zz;
-      if constexpr (ZST) {
-        zz = l.zz[0];
-      } else {
-        const float4 a = k.a, b = k.b;
-        zz = make_float4(epi_act(act_z, a.x * xv.x + b.x), epi_act(act_z, a.y * xv.y + b.y),
-                         epi_act(act_z, a.z * xv.z + b.z), epi_act(act_z, a.w * xv.w + b.w));
+    if constexpr (XH) xv = unpack_h4(l.xh[0]);
+    else xv = x.p ? l.xv[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (ZST || kRecomp) {
+      if (act_z) {
+        float4 zz;
+        if constexpr (ZST) {
+          zz = l.zz[0];
+        } else {
+          const float4 a = k.a[0], b = k.b[0];
+          zz = make_float4(epi_act(act_z, a.x * xv.x + b.x), epi_act(act_z, a.y * xv.y + b.y),
+                           epi_act(act_z, a.z * xv.z + b.z), epi_act(act_z, a.w * xv.w + b.w));
+        }
+        g.x *= act_grad(act_z, zz.x); g.y *= act_grad(act_z, zz.y);
+        g.z *= act_grad(act_z, zz.z); g.w *= act_grad(act_z, zz.w);
       }
-      g.x *= act_grad(act_z, zz.x); g.y *= act_grad(act_z, zz.y);
-      g.z *= act_grad(act_z, zz.z); g.w *= act_grad(act_z, zz.w);
     }
-    if (mean) {
+    if (has_bn()) {
       const float4 mu = k.mu, is = k.is;
       xhat = make_float4((xv.x - mu.x) * is.x, (xv.y - mu.y) * is.y, (xv.z - mu.z) * is.z, (xv.w - mu.w) * is.w);
     } else {
@@ -215,12 +246,12 @@ struct GradIn {
   }
 };
 
-template <bool MUL, bool ZST>
+template <bool MUL, bool ZST, bool XH = false>
 struct BnBwdReduceF {
-  static constexpr int kUnroll = (MUL || ZST) ? 2 : 4;
-  GradIn<MUL, ZST> in;
-  typedef typename GradIn<MUL, ZST>::Loaded Loaded;
-  typedef typename GradIn<MUL, ZST>::Consts Consts;
+  static constexpr int kUnroll = XH ? ((MUL || ZST) ? 3 : 6) : ((MUL || ZST) ? 2 : 4);
+  GradIn<MUL, ZST, XH> in;
+  typedef typename GradIn<MUL, ZST, XH>::Loaded Loaded;
+  typedef typename GradIn<MUL, ZST, XH>::Consts Consts;
   __device__ __forceinline__ void prep(int c, Consts& k) const { in.prep(c, k); }
   __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const { in.load(pix, hw, w, c, l); }
   __device__ __forceinline__ void consume(unsigned, unsigned, unsigned, int, const Consts& k, const Loaded& l, RedAcc<2>& a) const {
@@ -234,10 +265,10 @@ struct BnBwdReduceF {
 // With BN (in.mean != NULL): dx = gamma*invstd*(g - S1/M - xhat*S2/M) [* leaky'(x)].
 // Without BN: dx = g [* leaky'(x)]   (plain activation backward, e.g. the conv->LeakyReLU shortcuts).
 // GACC: g_out is accumulated into (its old value is one more operand stream).
-template <bool MUL, bool ZST, bool GACC>
+template <bool MUL, bool ZST, bool GACC, bool XH = false>
 struct BnBwdApplyF {
-  static constexpr int kUnroll = (MUL || ZST || GACC) ? 2 : 4;
-  GradIn<MUL, ZST> in;
+  static constexpr int kUnroll = XH ? ((MUL || ZST || GACC) ? 3 : 6) : ((MUL || ZST || GACC) ? 2 : 4);
+  GradIn<MUL, ZST, XH> in;
   const float* gamma;
   const double* red;
   double inv_count;
@@ -246,12 +277,12 @@ struct BnBwdApplyF {
   PV g_out;
   unsigned short* dx16;  // optional bf16 copy of dx (same element offsets): the operand of the kind::f16 dgrad / wgrad
   int write_dx32;        // 0: only the bf16 copy is stored (dx.p is then a placeholder base used for offsets only)
-  struct Loaded { typename GradIn<MUL, ZST>::Loaded i; float4 e[GACC ? 1 : 0]; };
-  struct Consts { typename GradIn<MUL, ZST>::Consts i; float4 gi, m1, m2; };
+  struct Loaded { typename GradIn<MUL, ZST, XH>::Loaded i; float4 e[GACC ? 1 : 0]; };
+  struct Consts { typename GradIn<MUL, ZST, XH>::Consts i; float4 gi, m1, m2; };
   __device__ __forceinline__ void prep(int c, Consts& k) const {
     in.prep(c, k.i);
     k.gi = k.m1 = k.m2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (in.mean) {
+    if (in.has_bn()) {
       const float4 gm = ld4(gamma + c);
       k.gi = make_float4(gm.x * k.i.is.x, gm.y * k.i.is.y, gm.z * k.i.is.z, gm.w * k.i.is.w);
       k.m1 = make_float4((float)(red[c] * inv_count), (float)(red[c + 1] * inv_count), (float)(red[c + 2] * inv_count),
@@ -262,7 +293,7 @@ struct BnBwdApplyF {
   }
   __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const {
     in.load(pix, hw, w, c, l.i);
-    if constexpr (GACC) l.e[0] = ld4(pv_at(g_out, pix, hw, w, c));
+    if constexpr (GACC) l.e[0] = ld4(pv_at_t<XH>(g_out, pix, hw, w, c));
   }
   __device__ __forceinline__ void consume(unsigned pix, unsigned hw, unsigned w, int c, const Consts& k, const Loaded& l,
                                           RedAcc<1>& a) const {
@@ -271,10 +302,10 @@ struct BnBwdApplyF {
     if (g_out.p) {
       float4 o = g;
       if constexpr (GACC) { o.x += l.e[0].x; o.y += l.e[0].y; o.z += l.e[0].z; o.w += l.e[0].w; }
-      *reinterpret_cast<float4*>(const_cast<float*>(pv_at(g_out, pix, hw, w, c))) = o;
+      *reinterpret_cast<float4*>(const_cast<float*>(pv_at_t<XH>(g_out, pix, hw, w, c))) = o;
     }
     float4 d = g;
-    if (in.mean) {
+    if (in.has_bn()) {
       d.x = k.gi.x * (g.x - k.m1.x - xh.x * k.m2.x);
       d.y = k.gi.y * (g.y - k.m1.y - xh.y * k.m2.y);
       d.z = k.gi.z * (g.z - k.m1.z - xh.z * k.m2.z);
@@ -289,7 +320,7 @@ struct BnBwdApplyF {
       d.x = round_tf32(d.x); d.y = round_tf32(d.y); d.z = round_tf32(d.z); d.w = round_tf32(d.w);
     }
     if (dx.p) {
-      float* dp = const_cast<float*>(pv_at(dx, pix, hw, w, c));
+      float* dp = const_cast<float*>(pv_at_t<XH>(dx, pix, hw, w, c));
       if (write_dx32) *reinterpret_cast<float4*>(dp) = d;
       if (dx16) {
         const __nv_bfloat162 a = __floats2bfloat162_rn(d.x, d.y), b = __floats2bfloat162_rn(d.z, d.w);
@@ -445,14 +476,17 @@ static int fill_grad_in(GI* gi, const pmfb_view* dy, const pmfb_view* mul, const
   return PMFB_OK;
 }
 
-template <bool MUL, bool ZST>
+template <bool MUL, bool ZST, bool XH>
 static int bn_bwd_reduce_t(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z, const pmfb_view* x,
                            const float* mean, const float* invstd, const float* alpha, const float* beta, int32_t n, int32_t h,
                            int32_t w, int32_t c, double* red, void* stream) {
-  typedef BnBwdReduceF<MUL, ZST> F;
+  typedef BnBwdReduceF<MUL, ZST, XH> F;
   F f;
   int rc = fill_grad_in(&f.in, dy, mul, z, act_z, x, mean, invstd, alpha, beta, h, w);
   if (rc) return rc;
+  if (XH && !(f.in.x.p && f.in.x.linear && f.in.dy.linear && (!ZST || f.in.z.linear)))
+    return fail(PMFB_ERR_INVALID, "bn_bwd_reduce16: x_half needs dense (pixel-linear) dy / x / z views");
+  if (XH && !MUL && !ZST && act_z) return fail(PMFB_ERR_INVALID, "bn_bwd_reduce16: x_half recomputes z only in the gated (mul) form");
   const long long npix = (long long)n * h * w;
   if (npix == 0) return PMFB_OK;
   RedGrid g = red_grid(chan_reduce_kernel<2, F>, npix, c / 4, 1);
@@ -479,9 +513,9 @@ struct ApplyArgs {
   void* dx16;
 };
 
-template <bool MUL, bool ZST, bool GACC>
+template <bool MUL, bool ZST, bool GACC, bool XH>
 static int bn_bwd_apply_t(const ApplyArgs& A) {
-  typedef BnBwdApplyF<MUL, ZST, GACC> F;
+  typedef BnBwdApplyF<MUL, ZST, GACC, XH> F;
   F f;
   int rc = fill_grad_in(&f.in, A.dy, A.mul, A.z, A.act_z, A.x, A.mean, A.invstd, A.alpha, A.beta, A.h, A.w);
   if (rc) return rc;
@@ -498,6 +532,11 @@ static int bn_bwd_apply_t(const ApplyArgs& A) {
   f.dx16 = static_cast<unsigned short*>(A.dx16);
   f.write_dx32 = A.dx ? 1 : 0;
   f.g_out = pv_out(A.g_out, A.g_sn, A.g_sy, A.g_sx, A.h, A.w);
+  if (XH && !(f.in.x.p && f.in.x.linear && f.in.dy.linear && (!ZST || f.in.z.linear) && (!f.dx.p || f.dx.linear) &&
+              (!f.g_out.p || f.g_out.linear)))
+    return fail(PMFB_ERR_INVALID, "bn_bwd_apply16: x_half needs dense (pixel-linear) dy / x / z / dx / g_out views");
+  if (XH && (!A.mean || (!MUL && !ZST && A.act_z)))
+    return fail(PMFB_ERR_INVALID, "bn_bwd_apply16: x_half needs BatchNorm statistics and recomputes z only in the gated (mul) form");
   RedGrid g = red_grid(chan_reduce_kernel<1, F>, npix, A.c / 4, 1);
   chan_reduce_kernel<1, F><<<g.grid, kRedThreads, 0, (cudaStream_t)A.stream>>>(f, (unsigned)npix, (unsigned)(A.h * A.w), (unsigned)A.w,
                                                                                A.c / 4, g.G, 0, A.colsum);
@@ -509,16 +548,32 @@ static int bn_bwd_apply_t(const ApplyArgs& A) {
   return PMFB_OK;
 }
 
+extern "C" int pmfb_bn_bwd_reduce16(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z,
+                                    const pmfb_view* x, const float* mean, const float* invstd, const float* alpha,
+                                    const float* beta, int32_t n, int32_t h, int32_t w, int32_t c, double* red, int32_t x_half,
+                                    void* stream) {
+  REQ(red && mean && c > 0 && c % 4 == 0, "bn_bwd_reduce: bad arguments");
+  const bool has_mul = mul && mul->ptr, has_z = act_z && z && z->ptr;
+  const int key = (has_mul ? 4 : 0) | (has_z ? 2 : 0) | (x_half ? 1 : 0);
+#define PMFB_RED(m, zz, xh) return bn_bwd_reduce_t<m, zz, xh>(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c, red, stream)
+  switch (key) {
+    case 0: PMFB_RED(false, false, false);
+    case 1: PMFB_RED(false, false, true);
+    case 2: PMFB_RED(false, true, false);
+    case 3: PMFB_RED(false, true, true);
+    case 4: PMFB_RED(true, false, false);
+    case 5: PMFB_RED(true, false, true);
+    case 6: PMFB_RED(true, true, false);
+    default: PMFB_RED(true, true, true);
+  }
+#undef PMFB_RED
+}
+
 extern "C" int pmfb_bn_bwd_reduce(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z,
                                   const pmfb_view* x, const float* mean, const float* invstd, const float* alpha,
                                   const float* beta, int32_t n, int32_t h, int32_t w, int32_t c, double* red,
                                   void* stream) {
-  REQ(red && mean && c > 0 && c % 4 == 0, "bn_bwd_reduce: bad arguments");
-  const bool has_mul = mul && mul->ptr, has_z = act_z && z && z->ptr;
-  if (has_mul) return has_z ? bn_bwd_reduce_t<true, true>(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c, red, stream)
-                            : bn_bwd_reduce_t<true, false>(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c, red, stream);
-  return has_z ? bn_bwd_reduce_t<false, true>(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c, red, stream)
-               : bn_bwd_reduce_t<false, false>(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c, red, stream);
+  return pmfb_bn_bwd_reduce16(dy, mul, z, act_z, x, mean, invstd, alpha, beta, n, h, w, c, red, 0, stream);
 }
 
 extern "C" int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z,
@@ -528,7 +583,7 @@ extern "C" int pmfb_bn_bwd_apply(const pmfb_view* dy, const pmfb_view* mul, cons
                                  int32_t round_out, float* dgamma, float* dbeta, double* colsum, float* g_out, int64_t g_sn,
                                  int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* stream) {
   return pmfb_bn_bwd_apply16(dy, mul, z, act_z, x, mean, invstd, alpha, beta, gamma, red, leaky_x, n, h, w, c, dx, d_sn, d_sy, d_sx,
-                             round_out, dgamma, dbeta, colsum, g_out, g_sn, g_sy, g_sx, g_accumulate, nullptr, stream);
+                             round_out, dgamma, dbeta, colsum, g_out, g_sn, g_sy, g_sx, g_accumulate, nullptr, 0, stream);
 }
 
 extern "C" int pmfb_bn_bwd_apply16(const pmfb_view* dy, const pmfb_view* mul, const pmfb_view* z, int32_t act_z,
@@ -536,7 +591,7 @@ extern "C" int pmfb_bn_bwd_apply16(const pmfb_view* dy, const pmfb_view* mul, co
                                    const float* beta, const float* gamma, const double* red, int32_t leaky_x, int32_t n,
                                    int32_t h, int32_t w, int32_t c, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
                                    int32_t round_out, float* dgamma, float* dbeta, double* colsum, float* g_out, int64_t g_sn,
-                                   int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* dx16, void* stream) {
+                                   int64_t g_sy, int64_t g_sx, int32_t g_accumulate, void* dx16, int32_t x_half, void* stream) {
   REQ(!dx16 || (reinterpret_cast<uintptr_t>(dx16) & 7) == 0, "bn_bwd_apply16: dx16 must be 8-byte aligned");
   REQ(dx || !dx16 || (((d_sn | d_sy | d_sx) % 4) == 0), "bn_bwd_apply16: bad dx16 strides");
   REQ(c > 0 && c % 4 == 0, "bn_bwd_apply: c=%d", c);
@@ -548,14 +603,27 @@ extern "C" int pmfb_bn_bwd_apply16(const pmfb_view* dy, const pmfb_view* mul, co
   ApplyArgs A{dy, mul, z, x, act_z, mean, invstd, alpha, beta, gamma, red, leaky_x, n, h, w, c, dx, d_sn, d_sy, d_sx, round_out,
               dgamma, dbeta, colsum, g_out, g_sn, g_sy, g_sx, stream, dx16};
   const int key = ((mul && mul->ptr) ? 4 : 0) | ((act_z && z && z->ptr) ? 2 : 0) | ((g_out && g_accumulate) ? 1 : 0);
+  if (x_half) {
+    REQ(x && x->ptr, "bn_bwd_apply16: x_half needs x");
+    switch (key) {
+      case 0: return bn_bwd_apply_t<false, false, false, true>(A);
+      case 1: return bn_bwd_apply_t<false, false, true, true>(A);
+      case 2: return bn_bwd_apply_t<false, true, false, true>(A);
+      case 3: return bn_bwd_apply_t<false, true, true, true>(A);
+      case 4: return bn_bwd_apply_t<true, false, false, true>(A);
+      case 5: return bn_bwd_apply_t<true, false, true, true>(A);
+      case 6: return bn_bwd_apply_t<true, true, false, true>(A);
+      default: return bn_bwd_apply_t<true, true, true, true>(A);
+    }
+  }
   switch (key) {
-    case 0: return bn_bwd_apply_t<false, false, false>(A);
-    case 1: return bn_bwd_apply_t<false, false, true>(A);
-    case 2: return bn_bwd_apply_t<false, true, false>(A);
-    case 3: return bn_bwd_apply_t<false, true, true>(A);
-    case 4: return bn_bwd_apply_t<true, false, false>(A);
-    case 5: return bn_bwd_apply_t<true, false, true>(A);
-    case 6: return bn_bwd_apply_t<true, true, false>(A);
-    default: return bn_bwd_apply_t<true, true, true>(A);
+    case 0: return bn_bwd_apply_t<false, false, false, false>(A);
+    case 1: return bn_bwd_apply_t<false, false, true, false>(A);
+    case 2: return bn_bwd_apply_t<false, true, false, false>(A);
+    case 3: return bn_bwd_apply_t<false, true, true, false>(A);
+    case 4: return bn_bwd_apply_t<true, false, false, false>(A);
+    case 5: return bn_bwd_apply_t<true, false, true, false>(A);
+    case 6: return bn_bwd_apply_t<true, true, false, false>(A);
+    default: return bn_bwd_apply_t<true, true, true, false>(A);
   }
 }

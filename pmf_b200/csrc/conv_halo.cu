@@ -13,6 +13,8 @@
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5 epilogue.
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "common.h"
 #include "epilogue.cuh"
 #include "ptx.cuh"
@@ -73,6 +75,11 @@ constexpr int kEpiStats = 16;
 // conv -> BN -> ReLU), ReLU, the post-activation affine alpha2/beta2 (SalsaNext conv -> LeakyReLU -> BN) and the second
 // residual r2 (ResContextBlock / ResBlock shortcut).  Only the combinations listed in launch_halo_variant exist.
 constexpr int kEpiA1 = 32, kEpiRelu = 64, kEpiA2B2 = 128, kEpiR2 = 256;
+// kEpiHalf (only with kEpiStats): the result is stored as fp16 -- the pre-BatchNorm activation of a training-mode
+// conv -> [LeakyReLU] -> BN layer, which only the BatchNorm passes read (never a convolution).  A warp's unit is then a
+// 32-pixel x 32-channel tile of 64-byte rows (SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3, conflict-free 16-byte stores),
+// stored by one bulk tensor store; the fused statistics are those of the ROUNDED values (what BatchNorm will normalise).
+constexpr int kEpiHalf = 512;
 constexpr int kHStatsC = 256;  // fused statistics: c_out <= 256 (2 x 256 fp64 accumulators in the unused alpha2/beta2 slots)
 
 // MMA issue loop of conv_fwd_halo_kernel (warp 1), specialised at compile time on the operand kind so that the issuing
@@ -301,6 +308,35 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
             if (lane == 0) bulk_wait_group_read0();
             __syncwarp();
           }
+          if constexpr ((EPI & kEpiHalf) != 0) {  // [+bias] [LeakyReLU] -> fp16, 8 channels per 16-byte store
+            if (valid) {
+              const uint32_t hrow = smem_u32(stage) + (uint32_t)lane * 64u;
+              const uint32_t hsw = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+              for (int i2 = 0; i2 < 4; ++i2) {
+                if (2 * i2 < nq) {
+                  uint32_t pk[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float a = v[8 * i2 + 2 * e], b = v[8 * i2 + 2 * e + 1];
+                    if constexpr ((EPI & kEpiB1) != 0) {
+                      a += sv[kHMaxC + c0 + 8 * i2 + 2 * e];
+                      b += sv[kHMaxC + c0 + 8 * i2 + 2 * e + 1];
+                    }
+                    if constexpr ((EPI & kEpiLeaky) != 0) {
+                      a = fmaxf(a, 0.01f * a);
+                      b = fmaxf(b, 0.01f * b);
+                    }
+                    const float m = 65504.f;  // saturate: an inf would poison the batch statistics
+                    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -m), m), fminf(fmaxf(b, -m), m));
+                    pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+                  }
+                  st_shared_v4(hrow + ((((uint32_t)i2) ^ hsw) << 4),
+                               make_float4(__uint_as_float(pk[0]), __uint_as_float(pk[1]), __uint_as_float(pk[2]), __uint_as_float(pk[3])));
+                }
+              }
+            }
+          } else
           if (valid) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -345,9 +381,22 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
           if constexpr ((EPI & kEpiStats) != 0) {
             const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
             if (lane < 4 * nq) {
+              float s1 = 0.f, s2 = 0.f;
+              if constexpr ((EPI & kEpiHalf) != 0) {  // column `lane` of the fp16 tile: 2-byte loads, 16 banks per row
+                const uint32_t col = smem_u32(stage) + (uint32_t)((lane & 7) << 1);
+                const uint32_t chunk = (uint32_t)(lane >> 3);
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                  if ((vmask >> r) & 1u) {
+                    const float t = __half2float(__ushort_as_half(
+                        ld_shared_u16(col + (uint32_t)r * 64u + ((chunk ^ ((uint32_t)(r >> 1) & 3u)) << 4))));
+                    s1 += t;
+                    s2 += t * t;
+                  }
+                }
+              } else {
               const uint32_t col = smem_u32(stage) + (uint32_t)((lane & 3) << 2);
               const uint32_t chunk = (uint32_t)(lane >> 2);
-              float s1 = 0.f, s2 = 0.f;
 #pragma unroll 8
               for (int r = 0; r < 32; ++r) {
                 if ((vmask >> r) & 1u) {
@@ -355,6 +404,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                   s1 += t;
                   s2 += t * t;
                 }
+              }
               }
               // fp64 shared accumulators: the order of the atomics must not show (a replayed step has to reproduce
               // an eager one, and near-constant channels turn fp32 ordering noise into percent-level BN changes)
@@ -482,6 +532,7 @@ static int launch_halo_variant(int epi, int grid, size_t smem, cudaStream_t stre
     PMFB_HV(0) PMFB_HV(1) PMFB_HV(2) PMFB_HV(3) PMFB_HV(4) PMFB_HV(5) PMFB_HV(6) PMFB_HV(7)
     PMFB_HV(8) PMFB_HV(9) PMFB_HV(12) PMFB_HV(13)
     PMFB_HV(16) PMFB_HV(17) PMFB_HV(24) PMFB_HV(25)
+    PMFB_HV(16 | kEpiHalf) PMFB_HV(17 | kEpiHalf) PMFB_HV(24 | kEpiHalf) PMFB_HV(25 | kEpiHalf)
     PMFB_HV(kEpiB1 | kEpiLeaky | kEpiA2B2 | kEpiRnd) PMFB_HV(kEpiB1 | kEpiLeaky | kEpiA2B2 | kEpiRnd | kEpiR2)
     PMFB_HV(kEpiA1 | kEpiB1 | kEpiRelu | kEpiRnd) PMFB_HV(kEpiA1 | kEpiB1 | kEpiRelu | kEpiRnd | kEpiR1)
     PMFB_HV(kEpiA1 | kEpiB1 | kEpiRnd)
@@ -525,6 +576,7 @@ int halo_fused_stats_ok(const pmfb_conv_desc* d) {
   const int epi = halo_fast_epi(d);
   if (epi == kEpiGeneric || (epi & ~(kEpiB1 | kEpiLeaky))) return 0;
   if ((reinterpret_cast<uintptr_t>(d->out) & 15) || d->o_sx % 4 || d->o_sy % 4 || d->o_sn % 4) return 0;
+  if (d->out_half && (d->c_out % 8 || d->o_sx % 8 || d->o_sy % 8 || d->o_sn % 8)) return 0;
   return d->c_out <= kHStatsC ? 1 : 0;
 }
 
@@ -667,9 +719,10 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   CUtensorMap tmo = tmw;  // placeholder when the direct-store path is used
   if (P.tma_store) {
     uint64_t odims[4] = {(uint64_t)d->c_out, (uint64_t)d->out_w, (uint64_t)d->out_h, (uint64_t)d->n_batch};
-    uint64_t ostr[3] = {(uint64_t)d->o_sx * 4, (uint64_t)d->o_sy * 4, (uint64_t)d->o_sn * 4};
+    const uint64_t osz = d->out_half ? 2 : 4;
+    uint64_t ostr[3] = {(uint64_t)d->o_sx * osz, (uint64_t)d->o_sy * osz, (uint64_t)d->o_sn * osz};
     uint32_t boxo[4] = {32, 8, 4, 1};
-    rc = make_tmap_f32(&tmo, d->out, 4, odims, ostr, boxo);
+    rc = d->out_half ? make_tmap_16(&tmo, d->out, 4, odims, ostr, boxo, false, true) : make_tmap_f32(&tmo, d->out, 4, odims, ostr, boxo);
     if (rc) return rc;
   }
   const size_t smem = (size_t)kHCtrlBytes + 2 * (size_t)P.a_bytes + (size_t)nsb * b_bytes + stage_total + 1024;
@@ -688,6 +741,9 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
     if (!halo_fused_stats_ok(d) || !P.tma_store || epi == kEpiGeneric)
       return fail(PMFB_ERR_INVALID, "conv halo: fused BN statistics are not available for this layer");
     epi |= kEpiStats;
+    if (d->out_half) epi |= kEpiHalf;
+  } else if (d->out_half) {
+    return fail(PMFB_ERR_INVALID, "conv halo: fp16 output exists only with the fused-statistics epilogue");
   }
   return launch_halo_variant(epi, grid, smem, (cudaStream_t)stream, tmx, tmw, tmo, P);
 }

@@ -353,6 +353,7 @@ extern "C" int pmfb_conv_fwd(const pmfb_conv_desc* d, void* stream) {
   }
   if (d->dtype != PMFB_DT_F32) return fail(PMFB_ERR_INVALID, "conv_fwd: 16-bit operands are only supported on the stride-1 halo kernel (query pmfb_conv16_ok)");
   if (d->bn_stats) return fail(PMFB_ERR_INVALID, "conv_fwd: fused BN statistics are not available for this layer (query pmfb_conv_fused_stats_ok)");
+  if (d->out_half) return fail(PMFB_ERR_INVALID, "conv_fwd: fp16 output exists only with the fused-statistics epilogue of the halo kernel");
   if (d->tile_w * d->tile_h != kTileM) return fail(PMFB_ERR_INVALID, "tile_w*tile_h must be 128");
   if (d->n_tile < 16 || d->n_tile > 256 || d->n_tile % 16)
     return fail(PMFB_ERR_INVALID, "n_tile=%d must be a multiple of 16 in [16,256]", d->n_tile);

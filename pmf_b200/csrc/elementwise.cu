@@ -80,10 +80,13 @@ struct PWParams {
 // OPS (bit 0: r1, bit 1: mul, bit 2: r2) is a compile-time mask of the per-pixel operands: the common launches (BN apply,
 // concat copies) carry none or one, and with the unused operand arrays compiled out the kernel fits 5-6 blocks per SM
 // instead of 2 (ncu: 104 registers, 24 % occupancy, 4.0 TB/s): more 16-byte loads in flight per SM.
-template <int OPS>
+// IH: the input view is an fp16 buffer (the pre-BatchNorm activation stored by the conv epilogue, pmfb_conv_desc.out_half);
+// its four values travel packed (8 bytes) and twice as many pixels are kept in flight.
+template <int OPS, bool IH>
 __global__ void __launch_bounds__(256)
 pointwise_kernel(PWParams P, unsigned npix, unsigned hw, unsigned w, int c4, int G) {
   constexpr bool kR1 = (OPS & 1) != 0, kMul = (OPS & 2) != 0, kR2 = (OPS & 4) != 0;
+  constexpr int U = (IH && OPS == 0) ? 8 : 4;  // BN apply without extra operand streams: twice the pixels in flight
   const int L = 256 / G;
   const int gl = threadIdx.x % G, pl = threadIdx.x / G;
   const int cg = blockIdx.y * G + gl;
@@ -93,23 +96,34 @@ pointwise_kernel(PWParams P, unsigned npix, unsigned hw, unsigned w, int c4, int
   const float4 a1 = P.alpha1 ? ld4(P.alpha1 + c) : one, b1 = P.beta1 ? ld4(P.beta1 + c) : zero;
   const float4 a2 = P.alpha2 ? ld4(P.alpha2 + c) : one, b2 = P.beta2 ? ld4(P.beta2 + c) : zero;
   const unsigned stride = gridDim.x * L;
-  for (unsigned p0 = blockIdx.x * L + pl; p0 < npix; p0 += 4 * stride) {
-    float4 v[4], r1[kR1 ? 4 : 1], mu[kMul ? 4 : 1], r2[kR2 ? 4 : 1];
+  for (unsigned p0 = blockIdx.x * L + pl; p0 < npix; p0 += U * stride) {
+    float4 v[IH ? 1 : U], r1[kR1 ? U : 1], mu[kMul ? U : 1], r2[kR2 ? U : 1];
+    uint2 vh[IH ? U : 1];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < U; ++k) {
       const unsigned p = p0 + k * stride;
       if (p < npix) {
-        v[k] = P.in.p ? ld4(pw_at(P.in, p, hw, w, c)) : zero;
-        if constexpr (kR1) r1[k] = ld4(pw_at(P.r1, p, hw, w, c));
+        if constexpr (IH)
+          vh[k] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(P.in.p) + ((long long)p * P.in.sx + c)));
+        else
+          v[k] = P.in.p ? ld4(pw_at(P.in, p, hw, w, c)) : zero;
+        if constexpr (kR1) r1[k] = ld4(IH ? P.r1.p + (long long)p * P.r1.sx + c : pw_at(P.r1, p, hw, w, c));
         if constexpr (kMul) mu[k] = ld4(pw_at(P.mul, p, hw, w, c));
-        if constexpr (kR2) r2[k] = ld4(pw_at(P.r2, p, hw, w, c));
+        if constexpr (kR2) r2[k] = ld4(IH ? P.r2.p + (long long)p * P.r2.sx + c : pw_at(P.r2, p, hw, w, c));
       }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < U; ++k) {
       const unsigned p = p0 + k * stride;
       if (p < npix) {
-        float4 o = v[k];
+        float4 o;
+        if constexpr (IH) {
+          const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&vh[k].x));
+          const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&vh[k].y));
+          o = make_float4(fa.x, fa.y, fb.x, fb.y);
+        } else {
+          o = v[k];
+        }
         o.x = o.x * a1.x + b1.x; o.y = o.y * a1.y + b1.y; o.z = o.z * a1.z + b1.z; o.w = o.w * a1.w + b1.w;
         if constexpr (kR1) { o.x += r1[k].x; o.y += r1[k].y; o.z += r1[k].z; o.w += r1[k].w; }
         if (P.act) { o.x = epi_act(P.act, o.x); o.y = epi_act(P.act, o.y); o.z = epi_act(P.act, o.z); o.w = epi_act(P.act, o.w); }
@@ -117,7 +131,7 @@ pointwise_kernel(PWParams P, unsigned npix, unsigned hw, unsigned w, int c4, int
         if constexpr (kMul) { o.x *= mu[k].x; o.y *= mu[k].y; o.z *= mu[k].z; o.w *= mu[k].w; }
         if constexpr (kR2) { o.x += r2[k].x; o.y += r2[k].y; o.z += r2[k].z; o.w += r2[k].w; }
         if (P.round_out) o = rnd4(o);
-        float* op = const_cast<float*>(pw_at(P.out, p, hw, w, c));
+        float* op = const_cast<float*>(IH ? P.out.p + (long long)p * P.out.sx + c : pw_at(P.out, p, hw, w, c));
         *reinterpret_cast<float4*>(op) = o;
         if (P.out16) *reinterpret_cast<uint2*>(P.out16 + (op - P.out.p)) = pack16(o, P.dt16);
         if (P.out16b) *reinterpret_cast<uint2*>(P.out16b + (op - P.out.p)) = pack16(o, PMFB_DT_BF16);
@@ -126,20 +140,20 @@ pointwise_kernel(PWParams P, unsigned npix, unsigned hw, unsigned w, int c4, int
   }
 }
 
-template <int OPS>
+template <int OPS, bool IH = false>
 static int launch_pointwise_t(const PWParams& P, long long npix, int h, int w, int c4, cudaStream_t stream) {
   const int G = c4 < 256 ? c4 : 256;
   const int L = 256 / G;
   const int gy = (c4 + G - 1) / G;
   static int per_sm = 0;
-  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pointwise_kernel<OPS>, 256, 0) != cudaSuccess || per_sm < 1))
+  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pointwise_kernel<OPS, IH>, 256, 0) != cudaSuccess || per_sm < 1))
     per_sm = 4;
   long long gx = (npix + (long long)L * 8 - 1) / ((long long)L * 8);
   long long cap = (148ll * per_sm) / gy;  // one resident wave
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  pointwise_kernel<OPS><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, stream>>>(P, (unsigned)npix, (unsigned)(h * w), (unsigned)w, c4, G);
+  pointwise_kernel<OPS, IH><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, stream>>>(P, (unsigned)npix, (unsigned)(h * w), (unsigned)w, c4, G);
   PMFB_LAUNCH_CHECK("pointwise_kernel");
   return PMFB_OK;
 }
@@ -675,12 +689,13 @@ static inline PWV pwv(const float* p, long long sn, long long sy, long long sx, 
 
 extern "C" int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n,
                               int32_t h, int32_t w, int32_t c, const pmfb_epilogue* epi, void* stream) {
-  return pmfb_pointwise16(in, out, o_sn, o_sy, o_sx, n, h, w, c, epi, nullptr, PMFB_DT_F16, nullptr, stream);
+  return pmfb_pointwise16(in, out, o_sn, o_sy, o_sx, n, h, w, c, epi, nullptr, PMFB_DT_F16, nullptr, 0, stream);
 }
 
 extern "C" int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n,
                                 int32_t h, int32_t w, int32_t c, const pmfb_epilogue* epi, void* out16, int32_t dtype16,
-                                void* out16_bf16, void* stream) {
+                                void* out16_bf16, int32_t in_half, void* stream) {
+  REQ(!in_half || (in && in->ptr), "pointwise16: in_half needs an input view");
   REQ(!out16_bf16 || (reinterpret_cast<uintptr_t>(out16_bf16) & 7) == 0, "pointwise16: the bf16 output must be 8-byte aligned");
   REQ(epi && c > 0 && c % 4 == 0, "pointwise: c=%d must be a positive multiple of 4", c);
   REQ(!out16 || ((dtype16 == PMFB_DT_F16 || dtype16 == PMFB_DT_BF16) && (reinterpret_cast<uintptr_t>(out16) & 7) == 0),
@@ -710,16 +725,14 @@ extern "C" int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, i
   P.out16b = static_cast<unsigned short*>(out16_bf16);
   const int ops = (P.r1.p ? 1 : 0) | (P.mul.p ? 2 : 0) | (P.r2.p ? 4 : 0);
   const cudaStream_t st = (cudaStream_t)stream;
+  REQ(!in_half || (P.in.linear && P.out.linear && (!P.r1.p || P.r1.linear) && (!P.r2.p || P.r2.linear)),
+      "pointwise16: in_half needs dense (pixel-linear) in / out / r1 / r2 views");
+#define PMFB_PW(o) case o: return in_half ? launch_pointwise_t<o, true>(P, npix, h, w, c / 4, st) : launch_pointwise_t<o, false>(P, npix, h, w, c / 4, st);
   switch (ops) {
-    case 0: return launch_pointwise_t<0>(P, npix, h, w, c / 4, st);
-    case 1: return launch_pointwise_t<1>(P, npix, h, w, c / 4, st);
-    case 2: return launch_pointwise_t<2>(P, npix, h, w, c / 4, st);
-    case 3: return launch_pointwise_t<3>(P, npix, h, w, c / 4, st);
-    case 4: return launch_pointwise_t<4>(P, npix, h, w, c / 4, st);
-    case 5: return launch_pointwise_t<5>(P, npix, h, w, c / 4, st);
-    case 6: return launch_pointwise_t<6>(P, npix, h, w, c / 4, st);
-    default: return launch_pointwise_t<7>(P, npix, h, w, c / 4, st);
+    PMFB_PW(0) PMFB_PW(1) PMFB_PW(2) PMFB_PW(3) PMFB_PW(4) PMFB_PW(5) PMFB_PW(6)
+    default: return in_half ? launch_pointwise_t<7, true>(P, npix, h, w, c / 4, st) : launch_pointwise_t<7, false>(P, npix, h, w, c / 4, st);
   }
+#undef PMFB_PW
 }
 
 extern "C" int pmfb_pack_input(const float* src, int64_t s_n, int64_t s_c, int64_t s_h, int64_t s_w, int32_t n, int32_t c,

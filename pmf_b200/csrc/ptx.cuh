@@ -104,6 +104,11 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t saddr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned short ld_shared_u16(uint32_t saddr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the newest 0 groups have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

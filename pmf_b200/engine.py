@@ -27,6 +27,9 @@ BN_EPS_DEFAULT = 1e-5
 H16_MIN_K = int(os.environ.get("PMFB_H16_MIN_K", "64"))
 H16_WGRAD_MIN = 64                                            # bf16 wgrad: one full 64-channel block per operand
 H16_WGRAD = os.environ.get("PMFB_H16_WGRAD", "1") != "0"
+# "f16" mode: the pre-BatchNorm activation of a training-mode conv -> [LeakyReLU] -> BN layer is STORED as fp16 by the conv
+# epilogue (pmfb_conv_desc.out_half); only the BatchNorm passes read it (apply, backward reduce, backward apply)
+PRE_BN_HALF = os.environ.get("PMFB_PRE_BN_HALF", "1") != "0"
 N_SM = 148
 
 
@@ -512,15 +515,20 @@ class Engine:
         n, h, w, c = dst.shape
         e = self._epi(**kw)
         sv = src if isinstance(src, View) else _view(src)
+        in_half = 1 if (torch.is_tensor(src) and src.dtype == torch.float16) else 0
         sh = shadow.shadow() if (self.h16 and shadow is not None) else None
         if sh is not None:
             assert tuple(sh.stride()) == tuple(dst.stride()), (sh.stride(), dst.stride())
             shb = shadow.shadow(True)
             L.call("pmfb_pointwise16", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
-                   C.byref(e), sh.data_ptr(), L.DT_F16, _p(shb), self.st)
+                   C.byref(e), sh.data_ptr(), L.DT_F16, _p(shb), in_half, self.st)
             shadow.shadow_mark()
             if shb is not None:
                 shadow.shadow_mark(True)
+            return
+        if in_half:
+            L.call("pmfb_pointwise16", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
+                   C.byref(e), None, L.DT_F16, None, 1, self.st)
             return
         L.call("pmfb_pointwise", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
                C.byref(e), self.st)
@@ -589,8 +597,10 @@ class Engine:
         return out
 
     def _conv_launch(self, x_t, c_in, stride2, w_packed, c_out, taps, n, out_h, out_w, out_t, epi, bn_stats=None, x16=None,
-                     w16=None, dt16=0):
+                     w16=None, dt16=0, out_half=False):
         """Returns True when ``bn_stats`` (2*c_out fp64 sums, zeroed) was accumulated by the conv's own epilogue.
+        ``out_half``: out_t is an fp16 buffer (pmfb_conv_desc.out_half, fused statistics only); returns None WITHOUT
+        launching when the library has no such epilogue for this layer.
         Precise mode: ``w_packed`` is the [hi|lo|hi] split packing over 3*roundup(c_in,32) channels and x is split here.
         "f16" mode: ``x16`` / ``w16`` are 16-bit shadows of x_t / w_packed (dt16 = DT_F16 or DT_BF16); they are used when the
         library accepts 16-bit operands for this geometry (pmfb_conv16_ok), else the fp32 operands."""
@@ -625,13 +635,16 @@ class Engine:
         elif x_t is None:
             raise L.PmfbError("pmf_b200: the library refused 16-bit operands for a layer planned on the bf16 backward path")
         fused = False
+        d.out_half = 1 if out_half else 0
         if bn_stats is not None and L.query("pmfb_conv_fused_stats_ok", C.byref(d)) == 1:
             d.bn_stats = bn_stats.data_ptr()
             fused = True
+        if out_half and not fused:
+            return None
         L.call("pmfb_conv_fwd", C.byref(d), self.st)
         return fused
 
-    def _conv_fwd(self, x, cp, out_t, epi, bn_stats=None):
+    def _conv_fwd(self, x, cp, out_t, epi, bn_stats=None, out_half=False):
         """out = epi(conv(x)); x: Act whose channel count equals cp.c_in_p."""
         e = self.cache.get(cp, self.record, self.st)
         n, h, w, cx = x.shape
@@ -645,7 +658,10 @@ class Engine:
         x16 = self._ensure_shadow(x) if (self.h16 and cp.stride == 1 and cp.c_in_p % 8 == 0 and cp.c_in_p >= H16_MIN_K
                                          and e.get("fwd16") is not None) else None
         fused = self._conv_launch(x.t, cp.c_in_p, cp.stride == 2, e["fwd3" if self.precise else "fwd"], cp.c_out_p, cp.fwd_taps(),
-                                  n, oh, ow, out_t, epi, bn_stats=bn_stats, x16=x16, w16=e.get("fwd16"), dt16=L.DT_F16)
+                                  n, oh, ow, out_t, epi, bn_stats=bn_stats, x16=x16, w16=e.get("fwd16"), dt16=L.DT_F16,
+                                  out_half=out_half)
+        if fused is None:
+            return None
         if self.record:
             self._wg_list.append(cp)
         return fused if bn_stats is not None else e
@@ -833,13 +849,20 @@ class Engine:
                bn.running_var.data_ptr(), bn.momentum, bn.eps, alpha.data_ptr(), beta.data_ptr(), None, None, self.st)
         return alpha, beta
 
-    def _conv_fwd_with_stats(self, x, cp, bn, out_t, epi):
-        """conv into out_t + the training-mode BatchNorm statistics of the result: fused into the conv's epilogue where
-        the library supports it (pmfb_conv_fused_stats_ok), else by a separate pmfb_bn_stats pass."""
+    def _conv_fwd_with_stats(self, x, cp, bn, shp, epi):
+        """(a, stats): a = epi(conv(x)), the pre-BatchNorm activation, and the training-mode BatchNorm statistics of it --
+        fused into the conv's epilogue where the library supports it (pmfb_conv_fused_stats_ok), else by a separate
+        pmfb_bn_stats pass.  "f16" mode: a is stored as fp16 where the fused epilogue exists (statistics of the stored
+        values); the three BatchNorm passes that read it take fp16."""
         assert cp.c_out_p == bn.c
         sums = self.d64.take(2 * bn.c)
-        fused = self._conv_fwd(x, cp, out_t, epi, bn_stats=sums)
-        return self._bn_train_affine(bn, out_t, sums=sums, have_sums=fused)
+        if self.h16 and PRE_BN_HALF and shp[3] % 8 == 0:
+            a = torch.empty(shp, device=self.device, dtype=torch.float16)
+            if self._conv_fwd(x, cp, a, epi, bn_stats=sums, out_half=True):
+                return a, self._bn_train_affine(bn, a, sums=sums, have_sums=True)
+        a = torch.empty(shp, device=self.device, dtype=torch.float32)
+        fused = self._conv_fwd(x, cp, a, epi, bn_stats=sums)
+        return a, self._bn_train_affine(bn, a, sums=sums, have_sums=fused)
 
     def _bn_train_affine(self, bn, a_t, sums=None, have_sums=False):
         n, h, w, c = a_t.shape
@@ -874,8 +897,9 @@ class Engine:
         n, h, w, c = a_t.shape
         red = self.d64.take(2 * c)
         dyv, mulv, zv, xv = _view(dy), (mul if isinstance(mul, View) else _view(mul)), _view(z), _view(a_t)
-        L.call("pmfb_bn_bwd_reduce", C.byref(dyv), C.byref(mulv), C.byref(zv), act_z, C.byref(xv), mean.data_ptr(),
-               invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), n, h, w, c, red.data_ptr(), self.st)
+        x_half = 1 if a_t.dtype == torch.float16 else 0
+        L.call("pmfb_bn_bwd_reduce16", C.byref(dyv), C.byref(mulv), C.byref(zv), act_z, C.byref(xv), mean.data_ptr(),
+               invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), n, h, w, c, red.data_ptr(), x_half, self.st)
         # "f16" mode: the same pass also stores d_pre as bf16, the operand of the kind::f16 dgrad / wgrad; the fp32 copy is
         # skipped when nothing reads it (need32 False)
         self._dpre16 = torch.empty((n, h, w, c), device=self.device, dtype=torch.bfloat16) if (self.h16 and c % 8 == 0 and c >= H16_MIN_K) else None
@@ -888,7 +912,7 @@ class Engine:
                invstd.data_ptr(), alpha.data_ptr(), beta.data_ptr(), bn.weight.detach().data_ptr(), red.data_ptr(), leaky_x,
                n, h, w, c, _p(d_pre), c * h * w, c * w, c, self.R, gw.data_ptr(),
                gb.data_ptr(), _p(cs), _p(g_out), *( (g_out.stride(0), g_out.stride(1), g_out.stride(2)) if g_out is not None
-                                                    else (0, 0, 0)), 1 if g_acc else 0, _p(self._dpre16), self.st)
+                                                    else (0, 0, 0)), 1 if g_acc else 0, _p(self._dpre16), x_half, self.st)
         self.param_grads[bn.name + ".weight"] = gw
         self.param_grads[bn.name + ".bias"] = gb
         return d_pre, cs
@@ -948,8 +972,7 @@ class Engine:
             alpha, beta = self._bn_eval_affine(bn)
             self._conv_fwd(x, cp, y.t, self._epi(beta1=e["bias"], act=ACT_LEAKY, alpha2=alpha, beta2=beta, r2=sc_t, rnd=1))
             return y
-        a = torch.empty(shp, device=self.device, dtype=torch.float32)
-        stats = self._conv_fwd_with_stats(x, cp, bn, a, self._epi(beta1=e["bias"], act=ACT_LEAKY))
+        a, stats = self._conv_fwd_with_stats(x, cp, bn, shp, self._epi(beta1=e["bias"], act=ACT_LEAKY))
         mv = None if mask is None else _chan_view(mask)
         self.pointwise(a, y.t, shadow=y, alpha1=stats[0], beta1=stats[1], r1=sc_t, mul=mv, rnd=1)
         if self.record:
@@ -992,8 +1015,7 @@ class Engine:
             self._conv_fwd(x, cp, y.t, self._epi(alpha1=alpha, beta1=beta, r1=id_t, act=post, mul=f_t, r2=pcd_t,
                                                  rnd=1 if rnd else 0))
             return y
-        c_t = torch.empty(shp, device=self.device, dtype=torch.float32)
-        stats = self._conv_fwd_with_stats(x, cp, bn, c_t, self._epi(beta1=e["bias"]))
+        c_t, stats = self._conv_fwd_with_stats(x, cp, bn, shp, self._epi(beta1=e["bias"]))
         mv = None if mask is None else _chan_view(mask)
         self.pointwise(c_t, y.t, shadow=y if rnd else None, alpha1=stats[0], beta1=stats[1], r1=id_t, act=post,
                        mul=f_t if gate is not None else mv, r2=pcd_t, rnd=1 if rnd else 0)

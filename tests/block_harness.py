@@ -42,7 +42,9 @@ def run_block(device, mod, build, oracle_fn, inputs, masks=None, train=True, mul
     params = {"b." + k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
               for k, v in sd.items()}
     xin = [x.clone().requires_grad_(True) for x in inputs]
-    ctx = po.Ctx(params, train=train, dropout={"b" + k: v for k, v in masks.items()}, tf32=tf32)
+    from pmf_b200 import engine as _eng
+    ctx = po.Ctx(params, train=train, dropout={"b" + k: v for k, v in masks.items()}, tf32=tf32,
+                 half_pre_bn=bool(E.h16 and _eng.PRE_BN_HALF))
     refs = oracle_fn(ctx, *xin)
     refs = refs if multi else (refs,)
     res = dict(fwd=[_rel(o, r.detach()) for o, r in zip(outs, refs)], dinput=[], dparam={}, stats={}, dinput_l2=[],

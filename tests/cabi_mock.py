@@ -503,8 +503,13 @@ def pmfb_pixel_scale(inp, n, h, w, c, pre, act, alpha, beta, r, post, out, o_sn,
 
 def pmfb_bn_bwd_apply16(*args):
     """The 16-bit shadow output belongs to the "f16" precision mode, which the engine only enables on CUDA tensors."""
-    assert not args[-2], "the numpy model does not emulate the 16-bit shadow outputs"
-    return pmfb_bn_bwd_apply(*args[:-2], args[-1])
+    assert not args[-3] and not args[-2], "the numpy model does not emulate the 16-bit shadow outputs / fp16 inputs"
+    return pmfb_bn_bwd_apply(*args[:-3], args[-1])
+
+
+def pmfb_bn_bwd_reduce16(*args):
+    assert not args[-2], "the numpy model does not emulate fp16 inputs"
+    return pmfb_bn_bwd_reduce(*args[:-2], args[-1])
 
 
 _IMPL = {k: v for k, v in globals().items() if k.startswith("pmfb_")}

@@ -144,17 +144,27 @@ def test_projection_full_size_collisions_and_empty(dev):
 _CASES = bh.block_cases(np.random.RandomState(7))
 
 
+@pytest.mark.parametrize("mode", ["tf32", "f16"])
 @pytest.mark.parametrize("case", _CASES, ids=[c[0] for c in _CASES])
-def test_block_forward_backward(dev, case):
-    """Every block of the graph on the real kernels vs the oracle with tf32-rounded conv operands + autograd.
-    fwd: max-norm 3e-3; gradients: relative L2 2e-2 (single activations within noise of a ReLU kink may flip)."""
+def test_block_forward_backward(dev, case, mode):
+    """Every block of the graph on the real kernels vs the oracle emulating the mode's rounding points + autograd.
+    "tf32": conv operands rounded to tf32 on both sides.  fwd: max-norm 3e-3; gradients: relative L2 3e-2 / 5e-2 (single
+    activations within noise of a ReLU kink may flip).
+    "f16" (the default training mode): additionally the pre-BatchNorm activations are stored in fp16 (the oracle rounds at
+    the same points, Ctx(half_pre_bn=True)) and >= 64-channel layers run from fp16 / bf16 operands, which the oracle
+    does not emulate.  These 128..512-pixel blocks are noise-dominated in that mode -- a value that lands on the other side
+    of an fp16 rounding boundary moves by 5e-4 and flips LeakyReLU / ReLU kinks downstream -- so the gradient bars are
+    looser; wiring errors are O(1) and are what the tf32 pass bounds tightly."""
+    import pmf_b200
     name, mod, build, oracle_fn, inputs, masks, multi, in_kw = case
-    res = bh.run_block("cuda:0", mod, build, oracle_fn, inputs, masks=masks, multi=multi, in_kw=in_kw, tf32=True)
-    _report("block/" + name, dict(fwd=res["fwd"], dinput_l2=res["dinput_l2"], dparam_l2_max=max(res["dparam_l2"].values()),
-                                  stats_max=max(list(res["stats"].values()) + [0.0])))
+    with pmf_b200.precision(mode):
+        res = bh.run_block("cuda:0", mod, build, oracle_fn, inputs, masks=masks, multi=multi, in_kw=in_kw, tf32=True)
+    _report("block/" + name + ("" if mode == "tf32" else "_f16"),
+            dict(fwd=res["fwd"], dinput_l2=res["dinput_l2"], dparam_l2_max=max(res["dparam_l2"].values()),
+                 stats_max=max(list(res["stats"].values()) + [0.0])))
     assert max(res["fwd"]) < 3e-3, res["fwd"]
-    assert max(res["dinput_l2"] + [0.0]) < 3e-2, res["dinput_l2"]
-    bad = {k: v for k, v in res["dparam_l2"].items() if v > 5e-2}
+    assert max(res["dinput_l2"] + [0.0]) < (3e-2 if mode == "tf32" else 5e-2), res["dinput_l2"]
+    bad = {k: v for k, v in res["dparam_l2"].items() if v > (5e-2 if mode == "tf32" else 1e-1)}
     assert not bad, bad
     bad = {k: v for k, v in res["stats"].items() if v > 2e-3}
     assert not bad, bad
