@@ -39,6 +39,7 @@ struct HCtrl {
 struct HaloK {
   int n_taps, ks;
   int tap_dw[PMFB_MAX_TAPS], tap_dh[PMFB_MAX_TAPS], tap_wi[PMFB_MAX_TAPS];
+  int tap_off[PMFB_MAX_TAPS];  // (descriptor units of 16 B) offset of tap t's window inside the halo tile
   int hx, hy, mt;
   int tiles_x, tiles_y, n_batch, n_blocks;
   int out_h, out_w, c_out, n_tile;
@@ -84,9 +85,14 @@ constexpr int kHStatsC = 256;  // fused statistics: c_out <= 256 (2 x 256 fp64 a
 
 // MMA issue loop of conv_fwd_halo_kernel (warp 1), specialised at compile time on the operand kind so that the issuing
 // warp's inner loop carries no per-instruction branch (instruction issue of this warp paces the tensor pipe).
+// MMA issue loop of conv_fwd_halo_kernel (warp 1), specialised at compile time on the operand kind.  Instruction issue of
+// this ONE warp paces the tensor pipe on the thin layers (ncu, 32 -> 32 channels at 480x640: ~145 warp instructions per
+// tap for 4 UMMAs of 80 cycles each), so the per-tap body is kept minimal: ring slot / phase / descriptor words advance
+// by adds (no modulo), the tap's window offset comes from a host-computed table, everything stays warp-uniform.
 template <bool F16>
 __device__ __forceinline__ void mma_issue_loop(const HaloK& P, HCtrl* ctrl, uint8_t* a_buf, uint8_t* b_buf, const int b_bytes,
-                                               const uint32_t tmem_base, const int total, const int pitch) {
+                                               const uint32_t tmem_base_in, const int total, const int pitch) {
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);  // provably warp-uniform
     const uint32_t idesc = F16 ? make_idesc_f16(128, (uint32_t)P.n_tile, P.dtype == PMFB_DT_BF16 ? 1u : 0u,
                                                 (P.dtype == PMFB_DT_BF16 || P.dtype == PMFB_DT_F16_BF16) ? 1u : 0u, 0, 0)
                                : make_idesc_tf32(128, (uint32_t)P.n_tile, 0, 0);
@@ -97,57 +103,64 @@ __device__ __forceinline__ void mma_issue_loop(const HaloK& P, HCtrl* ctrl, uint
     const uint32_t hi_b = (((8u * rb) >> 4) & 0x3FFFu) | (1u << 14) | lay;
     const uint32_t lbo_lo = (16u >> 4) << 16;
     const uint32_t j_step = ((uint32_t)(16 * pitch) * rb) >> 4;
-    uint32_t a_it = 0, b_it = 0, acc_it = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++acc_it) {
-      const uint32_t buf = acc_it % (uint32_t)P.nacc;
-      mbar_wait(&ctrl->tmem_empty[buf], ((acc_it / (uint32_t)P.nacc) & 1u) ^ 1u);
+    const int ks = P.ks, n_taps = P.n_taps, klast = P.klast;
+    const bool two = P.mt == 2;
+    const uint32_t n_tile = (uint32_t)P.n_tile, nsb = (uint32_t)P.nsb, nacc = (uint32_t)P.nacc;
+    const uint32_t acc_cols = (uint32_t)(P.mt * P.n_tile);
+    const uint32_t a_lo_buf0 = ((smem_u32(a_buf) & 0x3FFFFu) >> 4) | lbo_lo;
+    const uint32_t a_lo_buf1 = ((smem_u32(a_buf + (size_t)P.a_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
+    const uint32_t b_lo_first = ((smem_u32(b_buf) & 0x3FFFFu) >> 4) | lbo_lo;
+    const uint32_t b_step = (uint32_t)b_bytes >> 4;
+    uint32_t a_it = 0;
+    uint32_t st = 0, st_ph = 0, b_lo = b_lo_first;  // weight ring: slot, its phase, descriptor low word of the slot
+    uint32_t buf = 0, buf_ph = 0;                   // accumulator set and its phase
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      mbar_wait(&ctrl->tmem_empty[buf], buf_ph ^ 1u);
       tc_fence_after();
-      const uint32_t d_base = tmem_base + buf * (uint32_t)(P.mt * P.n_tile);
+      const uint32_t d_base = tmem_base + buf * acc_cols;
       uint32_t accumulate = 0;
-      for (int s = 0; s < P.ks; ++s) {
+      for (int s = 0; s < ks; ++s) {
         const uint32_t ab = a_it & 1u;
         mbar_wait(&ctrl->full_a[ab], (a_it >> 1) & 1u);
         tc_fence_after();
-        const uint32_t a_lo0 = ((smem_u32(a_buf + (size_t)ab * P.a_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
-        for (int t = 0; t < P.n_taps; ++t) {
-          const uint32_t st = b_it % (uint32_t)P.nsb;
-          mbar_wait(&ctrl->full_b[st], (b_it / (uint32_t)P.nsb) & 1u);
+        const uint32_t a_lo0 = ab ? a_lo_buf1 : a_lo_buf0;
+        const int nk = (s == ks - 1) ? klast : 4;
+        for (int t = 0; t < n_taps; ++t) {
+          mbar_wait(&ctrl->full_b[st], st_ph);
           tc_fence_after();
-          const uint32_t b_lo = ((smem_u32(b_buf + (size_t)st * b_bytes) & 0x3FFFFu) >> 4) | lbo_lo;
-          uint32_t a_lo = a_lo0 + (((uint32_t)((P.tap_dh[t] + P.hy) * pitch + P.tap_dw[t] + P.hx) * rb) >> 4);
-          uint32_t d_col = d_base;
-          if (s == P.ks - 1 && P.klast != 4) {  // partial last slab (e.g. 32 channels in a 64-channel 16-bit slab)
-            for (int j = 0; j < P.mt; ++j) {
-              for (int k = 0; k < P.klast; ++k) {
-                const uint64_t ad = (static_cast<uint64_t>(hi_a) << 32) | (a_lo + 2u * k);
-                const uint64_t bd = (static_cast<uint64_t>(hi_b) << 32) | (b_lo + 2u * k);
-                if constexpr (F16) umma_f16_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
-                else umma_tf32_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
-              }
-              a_lo += j_step;
-              d_col += (uint32_t)P.n_tile;
-            }
-          } else {
-            for (int j = 0; j < P.mt; ++j) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)P.tap_off[t];
+          if (nk == 4) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = (static_cast<uint64_t>(hi_a) << 32) | (a_lo + 2u * k);
-                const uint64_t bd = (static_cast<uint64_t>(hi_b) << 32) | (b_lo + 2u * k);
-                if constexpr (F16) umma_f16_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
-                else umma_tf32_warp(d_col, ad, bd, idesc, accumulate | (uint32_t)k);
-              }
-              a_lo += j_step;
-              d_col += (uint32_t)P.n_tile;
+            for (int k = 0; k < 4; ++k) umma_issue<F16>(d_base, a_lo + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc, accumulate | (uint32_t)k);
+            if (two) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_issue<F16>(d_base + n_tile, a_lo + j_step + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc, accumulate | (uint32_t)k);
             }
+          } else {  // partial last slab (e.g. 32 channels in a 64-channel 16-bit slab)
+            for (int k = 0; k < nk; ++k) umma_issue<F16>(d_base, a_lo + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc, accumulate | (uint32_t)k);
+            if (two)
+              for (int k = 0; k < nk; ++k)
+                umma_issue<F16>(d_base + n_tile, a_lo + j_step + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc, accumulate | (uint32_t)k);
           }
           accumulate = 1;
           umma_commit_warp(&ctrl->empty_b[st]);
-          ++b_it;
+          if (++st == nsb) {
+            st = 0;
+            st_ph ^= 1u;
+            b_lo = b_lo_first;
+          } else {
+            b_lo += b_step;
+          }
         }
         umma_commit_warp(&ctrl->empty_a[ab]);
         ++a_it;
       }
       umma_commit_warp(&ctrl->tmem_full[buf]);
+      if (++buf == nacc) {
+        buf = 0;
+        buf_ph ^= 1u;
+      }
     }
 }
 
@@ -208,7 +221,8 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t a_it = 0, b_it = 0;
+      uint32_t a_it = 0, st = 0, st_ph = 1;  // st_ph: parity to wait for on the slot's EMPTY barrier (first pass is free)
+      const uint32_t nsb = (uint32_t)P.nsb;
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         int r = w;
         const int nb = r % P.n_blocks; r /= P.n_blocks;
@@ -223,11 +237,13 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
           tma_load_5d(a_buf + (size_t)ab * P.a_bytes, &tmx, &ctrl->full_a[ab], s * P.kslab, x0 - P.hx, 0, y0 - P.hy, n_img);
           ++a_it;
           for (int t = 0; t < P.n_taps; ++t) {
-            const uint32_t st = b_it % (uint32_t)P.nsb;
-            mbar_wait(&ctrl->empty_b[st], ((b_it / (uint32_t)P.nsb) & 1u) ^ 1u);
+            mbar_wait(&ctrl->empty_b[st], st_ph);
             mbar_expect_tx(&ctrl->full_b[st], (uint32_t)b_bytes);
             tma_load_3d(b_buf + (size_t)st * b_bytes, &tmw, &ctrl->full_b[st], s * P.kslab, n0, P.tap_wi[t]);
-            ++b_it;
+            if (++st == nsb) {
+              st = 0;
+              st_ph ^= 1u;
+            }
           }
         }
       }
@@ -674,6 +690,8 @@ int launch_conv_halo(const pmfb_conv_desc* d, void* stream) {
   P.nacc = (2 * mt * n_tile <= 512) ? 2 : 1;
   P.tmem_cols = pow2_cols_h(P.nacc * mt * n_tile);
   const int rows = 16 * mt + 2 * P.hy, pitch = 8 + 2 * P.hx;
+  for (int i = 0; i < PMFB_MAX_TAPS; ++i)
+    P.tap_off[i] = i < d->n_taps ? (((P.tap_dh[i] + P.hy) * pitch + P.tap_dw[i] + P.hx) * P.row_bytes) >> 4 : 0;
   P.a_box_bytes = rows * pitch * P.row_bytes;
   P.a_bytes = (P.a_box_bytes + 1023) & ~1023;
   const int b_bytes = n_tile * P.row_bytes;

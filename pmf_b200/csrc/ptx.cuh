@@ -168,6 +168,34 @@ __device__ __forceinline__ void umma_f16_warp(uint32_t tmem_d, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One UMMA, descriptors passed as (low, high) 32-bit halves: the 64-bit operands are assembled by a register-pair move
+// inside the asm, so the issuing loop carries 32-bit adds only (no carry chains on the low words).
+template <bool F16>
+__device__ __forceinline__ void umma_issue(uint32_t d_col, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  if constexpr (F16) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_col),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_col),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
 __device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"

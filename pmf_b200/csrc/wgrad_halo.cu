@@ -127,9 +127,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_con
       const uint32_t lbo_a = (((uint32_t)P.a_blk_bytes >> 4) & 0x3FFFu) << 16;
       const uint32_t lbo_b = (((uint32_t)P.b_blk_bytes >> 4) & 0x3FFFu) << 16;
       const uint32_t a_kstep = (uint32_t)(2 * pitch * 128) >> 4;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % P.stages;
-        mbar_wait(&ctrl->full[s], (uint32_t)(it / P.stages) & 1u);
+      for (int it = 0, s = 0, s_ph = 0; it < iters; ++it) {
+        mbar_wait(&ctrl->full[s], (uint32_t)s_ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(tiles + (size_t)s * P.stage_bytes);
         const uint32_t a_lo00 = ((a_addr & 0x3FFFFu) >> 4) | lbo_a;
@@ -139,12 +138,14 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_con
           const uint32_t d_col = tmem_base + (uint32_t)((t - g_begin) * P.n_tile);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {  // two tile rows (16 pixels) per K step
-            const uint64_t ad = (static_cast<uint64_t>(hi_a) << 32) | (a_tap + (uint32_t)ks * a_kstep);
-            const uint64_t bd = (static_cast<uint64_t>(hi_b) << 32) | (b_lo0 + 128u * ks);
-            umma_f16_warp(d_col, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+            umma_issue<true>(d_col, a_tap + (uint32_t)ks * a_kstep, hi_a, b_lo0 + 128u * ks, hi_b, idesc, (uint32_t)(it | ks));
           }
         }
         umma_commit_warp(&ctrl->empty[s]);
+        if (++s == P.stages) {
+          s = 0;
+          s_ph ^= 1;
+        }
       }
       umma_commit_warp(&ctrl->tmem_full);
     } else if (warp == 1) {
@@ -153,9 +154,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_con
       const uint32_t hi = ((512u >> 4) & 0x3FFFu) | (1u << 14) | (1u << 29);  // SBO 512 B, SWIZZLE_128B_BASE32B
       const uint32_t lbo_a = (((uint32_t)P.a_blk_bytes >> 4) & 0x3FFFu) << 16;
       const uint32_t lbo_b = (((uint32_t)P.b_blk_bytes >> 4) & 0x3FFFu) << 16;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % P.stages;
-        mbar_wait(&ctrl->full[s], (uint32_t)(it / P.stages) & 1u);
+      for (int it = 0, s = 0, s_ph = 0; it < iters; ++it) {
+        mbar_wait(&ctrl->full[s], (uint32_t)s_ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(tiles + (size_t)s * P.stage_bytes);
         const uint32_t a_lo00 = (a_addr & 0x3FFFFu) >> 4;
@@ -166,12 +166,14 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_con
           const uint32_t d_col = tmem_base + (uint32_t)((t - g_begin) * P.n_tile);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {  // one tile row (8 pixels) per K step
-            const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_tap + (uint32_t)(ks * pitch * 8));
-            const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (b_lo0 + 64u * ks);
-            umma_tf32_warp(d_col, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+            umma_issue<false>(d_col, a_tap + (uint32_t)(ks * pitch * 8), hi, b_lo0 + 64u * ks, hi, idesc, (uint32_t)(it | ks));
           }
         }
         umma_commit_warp(&ctrl->empty[s]);
+        if (++s == P.stages) {
+          s = 0;
+          s_ph ^= 1;
+        }
       }
       umma_commit_warp(&ctrl->tmem_full);
     } else {
