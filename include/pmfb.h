@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PMFB_ABI_VERSION 5
+#define PMFB_ABI_VERSION 6
 #define PMFB_MAX_TAPS 9
 
 typedef enum {
@@ -132,6 +132,8 @@ typedef struct {
 } pmfb_wgrad_desc;
 
 int pmfb_abi_version(void);
+/* Multiprocessor count of the current device (148 on a B200): what the library sizes its grids from. */
+int pmfb_sm_count(void);
 const char* pmfb_last_error(void);
 /* 0 if an sm_100 device is present and the driver entry points resolve. */
 int pmfb_init(void);
@@ -209,6 +211,26 @@ int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, 
 int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n, int32_t h,
                      int32_t w, int32_t c, const pmfb_epilogue* epi, void* out16, int32_t dtype16, void* out16_bf16,
                      int32_t in_half, void* stream);
+
+/* Training-mode BatchNorm finalisation fused into the BN-apply pass (pmfb_pointwise16_bn): from the fp64 channel sums the
+ * convolution's epilogue accumulated (sums[0:C] = sum x, sums[C:2C] = sum x^2 over `count` pixels) every thread derives the
+ * affine of its own channels, alpha = gamma * invstd, beta = bias - mean * alpha, and uses it as the epilogue's
+ * alpha1 / beta1 (which must be NULL); one thread per channel also stores alpha / beta / mean / invstd (read by the backward
+ * passes) and updates the running statistics -- exactly pmfb_bn_finalize's arithmetic, without its launch. */
+typedef struct {
+  const double* sums;
+  int64_t count;
+  const float* gamma; /* may be NULL (= 1) */
+  const float* beta;  /* may be NULL (= 0) */
+  float* running_mean; /* may be NULL */
+  float* running_var;  /* may be NULL */
+  float momentum, eps;
+  float *alpha_out, *beta_out, *mean_out, *invstd_out; /* C floats each, all required */
+} pmfb_bn_fuse;
+/* in_half must be 1 (the fused form exists for the fp16 pre-BatchNorm activations of the "f16" mode). */
+int pmfb_pointwise16_bn(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n, int32_t h,
+                        int32_t w, int32_t c, const pmfb_epilogue* epi, void* out16, int32_t dtype16, void* out16_bf16,
+                        int32_t in_half, const pmfb_bn_fuse* bn, void* stream);
 
 /* 16-bit shadow of an fp32 NHWC view (c % 8 == 0; out16 has element strides o_sn / o_sy / o_sx, channel stride 1). */
 int pmfb_convert16(const pmfb_view* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out16, int64_t o_sn, int64_t o_sy,
@@ -305,9 +327,12 @@ int pmfb_d2f(const double* src, float* dst, int64_t n, float scale, int32_t accu
  * kind 1: MaxPool2d (torchvision stem), idx (uint8, dense [n,ho,wo,c]) records the arg-max tap 0..8.
  * chan_scale (may be NULL): per-(n,c) Dropout2d scale applied to the pooled value (salsanext.py:92-96:
  * pool(dropout(x)) == dropout-scale * pool(x) because the mask is constant over a plane). */
+/* out16 / out16_bf16 (here, in pmfb_pixel_shuffle and in pmfb_upsample2x; either may be NULL): fp16 / bf16 shadows of the
+ * result with the same ELEMENT strides as out -- the operands of the "f16" mode's kind::f16 convolutions and weight
+ * gradients, written by the producing pass instead of a separate pmfb_convert16. */
 int pmfb_pool3s2(int32_t kind, const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c,
                  const float* chan_scale, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, uint8_t* idx,
-                 int32_t round_out, void* stream);
+                 int32_t round_out, void* out16, void* out16_bf16, void* stream);
 int pmfb_pool3s2_bwd(int32_t kind, const pmfb_view* dy, int32_t n, int32_t h, int32_t w, int32_t c,
                      const float* chan_scale, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
                      const uint8_t* idx, int32_t accumulate, void* stream);
@@ -315,14 +340,15 @@ int pmfb_pool3s2_bwd(int32_t kind, const pmfb_view* dy, int32_t n, int32_t h, in
 /* PixelShuffle(2) (salsanext.py:137): out[n,2y+i,2x+j,c] = x[n,y,x,4c+2i+j] * (chan_scale ? chan_scale[n*C+c] : 1).
  * (h,w,c) are the OUTPUT-side channel count c and INPUT spatial dims h,w.  bwd is the inverse gather. */
 int pmfb_pixel_shuffle(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, const float* chan_scale,
-                       float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t round_out, void* stream);
+                       float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t round_out, void* out16, void* out16_bf16,
+                       void* stream);
 int pmfb_pixel_shuffle_bwd(const pmfb_view* dy, int32_t n, int32_t h, int32_t w, int32_t c,
                            const float* chan_scale, float* dx, int64_t d_sn, int64_t d_sy, int64_t d_sx,
                            int32_t accumulate, int32_t round_out, void* stream);
 
 /* nn.Upsample(scale_factor=2, mode="bilinear"), align_corners=False (pmf_net.py:191-210). (h,w) = input dims. */
 int pmfb_upsample2x(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, float* out, int64_t o_sn,
-                    int64_t o_sy, int64_t o_sx, int32_t round_out, void* stream);
+                    int64_t o_sy, int64_t o_sx, int32_t round_out, void* out16, void* out16_bf16, void* stream);
 int pmfb_upsample2x_bwd(const pmfb_view* dy, int32_t n, int32_t h, int32_t w, int32_t c, float* dx, int64_t d_sn,
                         int64_t d_sy, int64_t d_sx, int32_t accumulate, void* stream);
 

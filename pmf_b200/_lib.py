@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmf_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_TAPS = 9
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
@@ -40,6 +40,13 @@ class ConvDesc(C.Structure):
                 ("epi", Epilogue), ("bn_stats", C.c_void_p), ("dtype", i32), ("out_half", i32)]
 
 
+class BnFuse(C.Structure):
+    """pmfb_bn_fuse (include/pmfb.h): BatchNorm finalisation fused into the BN-apply pass."""
+    _fields_ = [("sums", C.c_void_p), ("count", i64), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("momentum", C.c_float), ("eps", C.c_float), ("alpha_out", C.c_void_p),
+                ("beta_out", C.c_void_p), ("mean_out", C.c_void_p), ("invstd_out", C.c_void_p)]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [("x", TmaSrc), ("dy", TmaSrc), ("c_in", i32), ("c_out", i32), ("n_taps", i32),
                 ("tap_dc", i32 * MAX_TAPS), ("tap_dw", i32 * MAX_TAPS), ("tap_dp", i32 * MAX_TAPS),
@@ -58,6 +65,7 @@ vp = C.c_void_p
 
 _SIGNATURES = {
     "pmfb_abi_version": ([], C.c_int),
+    "pmfb_sm_count": ([], C.c_int),
     "pmfb_last_error": ([], C.c_char_p),
     "pmfb_init": ([], C.c_int),
     "pmfb_conv_fwd": ([C.POINTER(ConvDesc), vp], C.c_int),
@@ -66,6 +74,8 @@ _SIGNATURES = {
     "pmfb_conv16_ok": ([C.POINTER(ConvDesc)], C.c_int),
     "pmfb_wgrad16_ok": ([C.POINTER(WgradDesc)], C.c_int),
     "pmfb_pointwise16": ([VP, vp, i64, i64, i64, i32, i32, i32, i32, C.POINTER(Epilogue), vp, i32, vp, i32, vp], C.c_int),
+    "pmfb_pointwise16_bn": ([VP, vp, i64, i64, i64, i32, i32, i32, i32, C.POINTER(Epilogue), vp, i32, vp, i32, C.POINTER(BnFuse), vp],
+                            C.c_int),
     "pmfb_bn_bwd_reduce16": ([VP, VP, VP, i32, VP, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, vp], C.c_int),
     "pmfb_convert16": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
     "pmfb_bn_bwd_apply16": ([VP, VP, VP, i32, VP, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i64, i64, i64,
@@ -88,11 +98,11 @@ _SIGNATURES = {
                            i32, vp, vp, vp, vp, i64, i64, i64, i32, vp], C.c_int),
     "pmfb_colsum": ([VP, i32, i32, i32, i32, i32, vp, vp], C.c_int),
     "pmfb_d2f": ([vp, vp, i64, C.c_float, i32, i32, vp], C.c_int),
-    "pmfb_pool3s2": ([i32, VP, i32, i32, i32, i32, vp, vp, i64, i64, i64, vp, i32, vp], C.c_int),
+    "pmfb_pool3s2": ([i32, VP, i32, i32, i32, i32, vp, vp, i64, i64, i64, vp, i32, vp, vp, vp], C.c_int),
     "pmfb_pool3s2_bwd": ([i32, VP, i32, i32, i32, i32, vp, vp, i64, i64, i64, vp, i32, vp], C.c_int),
-    "pmfb_pixel_shuffle": ([VP, i32, i32, i32, i32, vp, vp, i64, i64, i64, i32, vp], C.c_int),
+    "pmfb_pixel_shuffle": ([VP, i32, i32, i32, i32, vp, vp, i64, i64, i64, i32, vp, vp, vp], C.c_int),
     "pmfb_pixel_shuffle_bwd": ([VP, i32, i32, i32, i32, vp, vp, i64, i64, i64, i32, i32, vp], C.c_int),
-    "pmfb_upsample2x": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
+    "pmfb_upsample2x": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp, vp, vp], C.c_int),
     "pmfb_upsample2x_bwd": ([VP, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),
     "pmfb_softmax_nchw": ([VP, i32, i32, i32, i32, vp, vp], C.c_int),
     "pmfb_softmax_nchw_bwd": ([vp, vp, i32, i32, i32, i32, vp, i64, i64, i64, i32, vp], C.c_int),

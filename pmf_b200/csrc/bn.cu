@@ -97,7 +97,7 @@ chan_reduce_kernel(F f, unsigned npix, unsigned hw, unsigned w, int c4, int G, i
     const int c = cg * 4;
     unsigned p = blockIdx.x * L + pl;
     typename F::Consts k;
-    f.prep(c, k);  // per-channel constants of this thread's four channels, loaded once
+    f.prep(c, k, blockIdx.x == 0 && pl == 0 && blockIdx.z == 0);  // per-channel constants of this thread's four channels, loaded once
     constexpr int U = F::kUnroll;
     for (; p + (U - 1) * stride < npix; p += U * stride) {
       typename F::Loaded l[U];
@@ -141,7 +141,7 @@ struct StatsF {
   PV x;
   struct Loaded { float4 v; };
   struct Consts {};
-  __device__ __forceinline__ void prep(int, Consts&) const {}
+  __device__ __forceinline__ void prep(int, Consts&, bool) const {}
   __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const {
     l.v = ld4(pv_at(x, pix, hw, w, c));
   }
@@ -156,7 +156,7 @@ struct ColsumF {
   PV x;
   struct Loaded { float4 v; };
   struct Consts {};
-  __device__ __forceinline__ void prep(int, Consts&) const {}
+  __device__ __forceinline__ void prep(int, Consts&, bool) const {}
   __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const {
     l.v = ld4(pv_at(x, pix, hw, w, c));
   }
@@ -200,7 +200,7 @@ struct GradIn {
   static constexpr bool kRecomp = !ZST && (MUL || !XH);
   struct Consts { float4 mu, is, a[kRecomp ? 1 : 0], b[kRecomp ? 1 : 0]; };
   __device__ __forceinline__ bool has_bn() const { return XH || mean != nullptr; }
-  __device__ __forceinline__ void prep(int c, Consts& k) const {
+  __device__ __forceinline__ void prep(int c, Consts& k, bool = false) const {
     k.mu = k.is = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_bn()) { k.mu = ld4(mean + c); k.is = ld4(invstd + c); }
     if constexpr (kRecomp) {
@@ -252,7 +252,7 @@ struct BnBwdReduceF {
   GradIn<MUL, ZST, XH> in;
   typedef typename GradIn<MUL, ZST, XH>::Loaded Loaded;
   typedef typename GradIn<MUL, ZST, XH>::Consts Consts;
-  __device__ __forceinline__ void prep(int c, Consts& k) const { in.prep(c, k); }
+  __device__ __forceinline__ void prep(int c, Consts& k, bool) const { in.prep(c, k); }
   __device__ __forceinline__ void load(unsigned pix, unsigned hw, unsigned w, int c, Loaded& l) const { in.load(pix, hw, w, c, l); }
   __device__ __forceinline__ void consume(unsigned, unsigned, unsigned, int, const Consts& k, const Loaded& l, RedAcc<2>& a) const {
     float4 g, xh, xv;
@@ -271,6 +271,8 @@ struct BnBwdApplyF {
   GradIn<MUL, ZST, XH> in;
   const float* gamma;
   const double* red;
+  float* dgamma;  // BatchNorm parameter gradients, stored by the owner threads (16-byte aligned) or NULL
+  float* dbeta;
   double inv_count;
   int C, leaky_x, round_out;
   PV dx;
@@ -279,10 +281,17 @@ struct BnBwdApplyF {
   int write_dx32;        // 0: only the bf16 copy is stored (dx.p is then a placeholder base used for offsets only)
   struct Loaded { typename GradIn<MUL, ZST, XH>::Loaded i; float4 e[GACC ? 1 : 0]; };
   struct Consts { typename GradIn<MUL, ZST, XH>::Consts i; float4 gi, m1, m2; };
-  __device__ __forceinline__ void prep(int c, Consts& k) const {
+  // owner: exactly one thread per 4-channel group of the launch -- it also stores the BatchNorm parameter gradients
+  // (dbeta = sum g, dgamma = sum g * xhat: the reduce pass's sums), which used to be a separate tiny launch
+  __device__ __forceinline__ void prep(int c, Consts& k, bool owner) const {
     in.prep(c, k.i);
     k.gi = k.m1 = k.m2 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (in.has_bn()) {
+      if (owner) {
+        if (dbeta) *reinterpret_cast<float4*>(dbeta + c) = make_float4((float)red[c], (float)red[c + 1], (float)red[c + 2], (float)red[c + 3]);
+        if (dgamma)
+          *reinterpret_cast<float4*>(dgamma + c) = make_float4((float)red[C + c], (float)red[C + c + 1], (float)red[C + c + 2], (float)red[C + c + 3]);
+      }
       const float4 gm = ld4(gamma + c);
       k.gi = make_float4(gm.x * k.i.is.x, gm.y * k.i.is.y, gm.z * k.i.is.z, gm.w * k.i.is.w);
       k.m1 = make_float4((float)(red[c] * inv_count), (float)(red[c + 1] * inv_count), (float)(red[c + 2] * inv_count),
@@ -523,6 +532,9 @@ static int bn_bwd_apply_t(const ApplyArgs& A) {
   if (npix == 0) return PMFB_OK;
   f.gamma = A.gamma;
   f.red = A.red;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(A.dgamma) | reinterpret_cast<uintptr_t>(A.dbeta)) & 15) == 0;
+  f.dgamma = (A.mean && vec_ok) ? A.dgamma : nullptr;
+  f.dbeta = (A.mean && vec_ok) ? A.dbeta : nullptr;
   f.inv_count = 1.0 / (double)npix;
   f.C = A.c;
   f.leaky_x = A.leaky_x;
@@ -541,7 +553,7 @@ static int bn_bwd_apply_t(const ApplyArgs& A) {
   chan_reduce_kernel<1, F><<<g.grid, kRedThreads, 0, (cudaStream_t)A.stream>>>(f, (unsigned)npix, (unsigned)(A.h * A.w), (unsigned)A.w,
                                                                                A.c / 4, g.G, 0, A.colsum);
   PMFB_LAUNCH_CHECK("bn_bwd_apply");
-  if (A.mean && (A.dgamma || A.dbeta)) {
+  if (A.mean && (A.dgamma || A.dbeta) && !vec_ok) {  // unaligned parameter-gradient storage: the separate copy
     red_to_params_kernel<<<(A.c + 127) / 128, 128, 0, (cudaStream_t)A.stream>>>(A.red, A.c, A.dgamma, A.dbeta);
     PMFB_LAUNCH_CHECK("red_to_params");
   }

@@ -102,7 +102,21 @@ int make_tmap_16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* di
 
 }  // namespace pmfb
 
+namespace pmfb {
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else return 148;
+  }
+  return n;
+}
+}  // namespace pmfb
+
 extern "C" {
+
+int pmfb_sm_count(void) { return pmfb::sm_count(); }
 
 int pmfb_abi_version(void) { return PMFB_ABI_VERSION; }
 

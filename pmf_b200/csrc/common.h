@@ -10,6 +10,8 @@
 namespace pmfb {
 
 void set_error(const char* fmt, ...);
+// Multiprocessor count of the current device (cached; 148 on a B200): every grid is sized from it.
+int sm_count();
 int fail(int code, const char* fmt, ...);
 
 // cuTensorMapEncodeTiled resolved through cudaGetDriverEntryPoint (no link-time libcuda dependency).

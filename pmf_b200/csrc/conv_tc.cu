@@ -112,9 +112,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
     const uint32_t idesc = make_idesc_tf32(kTileM, (uint32_t)P.n_tile, 0, 0);
     const uint32_t hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
     const uint32_t lbo_lo = (16u >> 4) << 16;
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % P.stages;
-      const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
+    uint32_t ph = 0;
+    for (int it = 0, s = 0; it < iters; ++it) {
       mbar_wait(&ctrl->full[s], ph);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
@@ -122,11 +121,13 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constan
       const uint32_t b_lo = (((a_addr + kSlabBytes) & 0x3FFFFu) >> 4) | lbo_lo;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_lo + 2u * k);
-        const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (b_lo + 2u * k);
-        umma_tf32_warp(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        umma_issue<false>(tmem_base, a_lo + 2u * k, hi, b_lo + 2u * k, hi, idesc, (uint32_t)(it | k));
       }
       umma_commit_warp(&ctrl->empty[s]);
+      if (++s == P.stages) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
     umma_commit_warp(&ctrl->tmem_full);
   } else {
@@ -253,9 +254,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
       // atoms (SBO = 512 B); LBO = distance between 32-channel blocks; a K step advances the start by 1024 B.
       const uint32_t hi = ((512u >> 4) & 0x3FFFu) | (1u << 14) | (1u << 29);
       const uint32_t lbo_lo = (((uint32_t)kBoxBytes >> 4) & 0x3FFFu) << 16;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % P.stages;
-        const uint32_t ph = (uint32_t)(it / P.stages) & 1u;
+      uint32_t ph = 0;
+      for (int it = 0, s = 0; it < iters; ++it) {
         mbar_wait(&ctrl->full[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(tiles + (size_t)s * stage_bytes);
@@ -263,11 +263,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
         const uint32_t b_lo = (((a_addr + 4 * kBoxBytes) & 0x3FFFFu) >> 4) | lbo_lo;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = (static_cast<uint64_t>(hi) << 32) | (a_lo + 64u * k);
-          const uint64_t bd = (static_cast<uint64_t>(hi) << 32) | (b_lo + 64u * k);
-          umma_tf32_warp(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_issue<false>(tmem_base, a_lo + 64u * k, hi, b_lo + 64u * k, hi, idesc, (uint32_t)(it | k));
         }
         umma_commit_warp(&ctrl->empty[s]);
+        if (++s == P.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
       umma_commit_warp(&ctrl->tmem_full);
     } else {

@@ -33,7 +33,8 @@ __device__ __forceinline__ uint2 pack16(float4 v, int dt) {
   return r;
 }
 
-static inline int grid_for(long long work, int threads, int max_blocks = 148 * 16) {
+static inline int grid_for(long long work, int threads, int max_blocks = 0) {
+  if (max_blocks <= 0) max_blocks = sm_count() * 16;
   long long b = (work + threads - 1) / threads;
   if (b < 1) b = 1;
   if (b > max_blocks) b = max_blocks;
@@ -75,6 +76,7 @@ struct PWParams {
   unsigned short* out16;  // optional 16-bit shadow of the result (same element offsets as out)
   int dt16;
   unsigned short* out16b;  // optional second shadow, always bf16 (the wgrad operand)
+  pmfb_bn_fuse bn;         // BNF kernels: BatchNorm finalisation from the fused channel sums (see include/pmfb.h)
 };
 
 // OPS (bit 0: r1, bit 1: mul, bit 2: r2) is a compile-time mask of the per-pixel operands: the common launches (BN apply,
@@ -82,7 +84,9 @@ struct PWParams {
 // instead of 2 (ncu: 104 registers, 24 % occupancy, 4.0 TB/s): more 16-byte loads in flight per SM.
 // IH: the input view is an fp16 buffer (the pre-BatchNorm activation stored by the conv epilogue, pmfb_conv_desc.out_half);
 // its four values travel packed (8 bytes) and twice as many pixels are kept in flight.
-template <int OPS, bool IH>
+// BNF (with IH): alpha1 / beta1 are derived here from the convolution's fused channel sums (pmfb_bn_fuse) instead of being
+// read from the vectors a separate bn_finalize launch would have written.
+template <int OPS, bool IH, bool BNF = false>
 __global__ void __launch_bounds__(256)
 pointwise_kernel(PWParams P, unsigned npix, unsigned hw, unsigned w, int c4, int G) {
   constexpr bool kR1 = (OPS & 1) != 0, kMul = (OPS & 2) != 0, kR2 = (OPS & 4) != 0;
@@ -93,7 +97,45 @@ pointwise_kernel(PWParams P, unsigned npix, unsigned hw, unsigned w, int c4, int
   if (pl >= L || cg >= c4) return;
   const int c = cg * 4;
   const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 a1 = P.alpha1 ? ld4(P.alpha1 + c) : one, b1 = P.beta1 ? ld4(P.beta1 + c) : zero;
+  float4 a1 = one, b1 = zero;
+  if constexpr (BNF) {  // pmfb_bn_finalize's arithmetic for this thread's four channels
+    const int C = c4 * 4;
+    const double cnt = (double)P.bn.count;
+    float al[4], be[4], mu[4], is[4];
+    const bool owner = blockIdx.x == 0 && pl == 0;  // one thread per channel group stores the vectors / running statistics
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double m = P.bn.sums[c + j] / cnt;
+      double v = P.bn.sums[C + c + j] / cnt - m * m;
+      if (v < 0.0) v = 0.0;
+      const float mean = (float)m, var = (float)v;
+      const float invstd = 1.f / sqrtf(var + P.bn.eps);
+      const float g = P.bn.gamma ? P.bn.gamma[c + j] : 1.f;
+      const float b = P.bn.beta ? P.bn.beta[c + j] : 0.f;
+      al[j] = g * invstd;
+      be[j] = b - mean * al[j];
+      mu[j] = mean;
+      is[j] = invstd;
+      if (owner) {
+        if (P.bn.running_mean) P.bn.running_mean[c + j] = (1.f - P.bn.momentum) * P.bn.running_mean[c + j] + P.bn.momentum * mean;
+        if (P.bn.running_var) {
+          const float unbiased = cnt > 1.0 ? (float)(v * cnt / (cnt - 1.0)) : var;
+          P.bn.running_var[c + j] = (1.f - P.bn.momentum) * P.bn.running_var[c + j] + P.bn.momentum * unbiased;
+        }
+      }
+    }
+    a1 = make_float4(al[0], al[1], al[2], al[3]);
+    b1 = make_float4(be[0], be[1], be[2], be[3]);
+    if (owner) {
+      *reinterpret_cast<float4*>(P.bn.alpha_out + c) = a1;
+      *reinterpret_cast<float4*>(P.bn.beta_out + c) = b1;
+      *reinterpret_cast<float4*>(P.bn.mean_out + c) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+      *reinterpret_cast<float4*>(P.bn.invstd_out + c) = make_float4(is[0], is[1], is[2], is[3]);
+    }
+  } else {
+    if (P.alpha1) a1 = ld4(P.alpha1 + c);
+    if (P.beta1) b1 = ld4(P.beta1 + c);
+  }
   const float4 a2 = P.alpha2 ? ld4(P.alpha2 + c) : one, b2 = P.beta2 ? ld4(P.beta2 + c) : zero;
   const unsigned stride = gridDim.x * L;
   for (unsigned p0 = blockIdx.x * L + pl; p0 < npix; p0 += U * stride) {
@@ -140,20 +182,20 @@ pointwise_kernel(PWParams P, unsigned npix, unsigned hw, unsigned w, int c4, int
   }
 }
 
-template <int OPS, bool IH = false>
+template <int OPS, bool IH = false, bool BNF = false>
 static int launch_pointwise_t(const PWParams& P, long long npix, int h, int w, int c4, cudaStream_t stream) {
   const int G = c4 < 256 ? c4 : 256;
   const int L = 256 / G;
   const int gy = (c4 + G - 1) / G;
   static int per_sm = 0;
-  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pointwise_kernel<OPS, IH>, 256, 0) != cudaSuccess || per_sm < 1))
+  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pointwise_kernel<OPS, IH, BNF>, 256, 0) != cudaSuccess || per_sm < 1))
     per_sm = 4;
   long long gx = (npix + (long long)L * 8 - 1) / ((long long)L * 8);
-  long long cap = (148ll * per_sm) / gy;  // one resident wave
+  long long cap = ((long long)sm_count() * per_sm) / gy;  // one resident wave
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  pointwise_kernel<OPS, IH><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, stream>>>(P, (unsigned)npix, (unsigned)(h * w), (unsigned)w, c4, G);
+  pointwise_kernel<OPS, IH, BNF><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, stream>>>(P, (unsigned)npix, (unsigned)(h * w), (unsigned)w, c4, G);
   PMFB_LAUNCH_CHECK("pointwise_kernel");
   return PMFB_OK;
 }
@@ -288,7 +330,8 @@ __global__ void d2f_kernel(const double* __restrict__ src, float* __restrict__ d
 // ------------------------------------------------------------------------------------ 3x3 s2 p1 pooling
 __global__ void __launch_bounds__(256)
 pool3s2_kernel(int kind, EpiView xin, int n, int h, int w, int c4, const float* __restrict__ chan_scale, float* out,
-               long long o_sn, long long o_sy, long long o_sx, uint8_t* idx, int round_out) {
+               long long o_sn, long long o_sy, long long o_sx, uint8_t* idx, int round_out, unsigned short* out16,
+               unsigned short* out16b) {
   const int ho = h / 2, wo = w / 2;
   const long long total = (long long)n * ho * wo * c4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -327,7 +370,10 @@ pool3s2_kernel(int kind, EpiView xin, int n, int h, int w, int c4, const float* 
       acc.x *= sc.x; acc.y *= sc.y; acc.z *= sc.z; acc.w *= sc.w;
     }
     if (round_out) acc = rnd4(acc);
-    *reinterpret_cast<float4*>(out + (long long)ni * o_sn + (long long)yo * o_sy + (long long)xo * o_sx + c) = acc;
+    const long long off = (long long)ni * o_sn + (long long)yo * o_sy + (long long)xo * o_sx + c;
+    *reinterpret_cast<float4*>(out + off) = acc;
+    if (out16) *reinterpret_cast<uint2*>(out16 + off) = pack16(acc, PMFB_DT_F16);
+    if (out16b) *reinterpret_cast<uint2*>(out16b + off) = pack16(acc, PMFB_DT_BF16);
   }
 }
 
@@ -393,7 +439,7 @@ pool3s2_bwd_kernel(int kind, EpiView dy, int n, int h, int w, int c4, const floa
 // thread = (input pixel, group of 4 OUTPUT channels): reads 16 contiguous input channels, writes 4 pixels x float4.
 __global__ void __launch_bounds__(256)
 pixel_shuffle_kernel(EpiView xin, int n, int h, int w, int c4, const float* __restrict__ chan_scale, float* out,
-                     long long o_sn, long long o_sy, long long o_sx, int round_out) {
+                     long long o_sn, long long o_sy, long long o_sx, int round_out, unsigned short* out16, unsigned short* out16b) {
   const long long total = (long long)n * h * w * c4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(i % c4);
@@ -415,8 +461,10 @@ pixel_shuffle_kernel(EpiView xin, int n, int h, int w, int c4, const float* __re
     for (int q = 0; q < 4; ++q) {
       const int ii = q >> 1, jj = q & 1;
       float4 v = round_out ? rnd4(o[q]) : o[q];
-      *reinterpret_cast<float4*>(out + (long long)ni * o_sn + (long long)(2 * y + ii) * o_sy + (long long)(2 * x + jj) * o_sx +
-                                 cg * 4) = v;
+      const long long off = (long long)ni * o_sn + (long long)(2 * y + ii) * o_sy + (long long)(2 * x + jj) * o_sx + cg * 4;
+      *reinterpret_cast<float4*>(out + off) = v;
+      if (out16) *reinterpret_cast<uint2*>(out16 + off) = pack16(v, PMFB_DT_F16);
+      if (out16b) *reinterpret_cast<uint2*>(out16b + off) = pack16(v, PMFB_DT_BF16);
     }
   }
 }
@@ -469,7 +517,7 @@ __device__ __forceinline__ void up2_src(int o, int size, int& i0, int& i1, float
 }
 
 __global__ void __launch_bounds__(256)
-upsample2x_kernel(EpiView xin, int n, int h, int w, int c4, float* out, long long o_sn, long long o_sy, long long o_sx,
+upsample2x_kernel(EpiView xin, int n, int h, int w, int c4, unsigned short* out16, unsigned short* out16b, float* out, long long o_sn, long long o_sy, long long o_sx,
                   int round_out) {
   const int ho = 2 * h, wo = 2 * w;
   const long long total = (long long)n * ho * wo * c4;
@@ -496,7 +544,10 @@ upsample2x_kernel(EpiView xin, int n, int h, int w, int c4, float* out, long lon
     o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
     o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
     if (round_out) o = rnd4(o);
-    *reinterpret_cast<float4*>(out + (long long)ni * o_sn + (long long)yo * o_sy + (long long)xo * o_sx + cg * 4) = o;
+    const long long off = (long long)ni * o_sn + (long long)yo * o_sy + (long long)xo * o_sx + cg * 4;
+    *reinterpret_cast<float4*>(out + off) = o;
+    if (out16) *reinterpret_cast<uint2*>(out16 + off) = pack16(o, PMFB_DT_F16);
+    if (out16b) *reinterpret_cast<uint2*>(out16b + off) = pack16(o, PMFB_DT_BF16);
   }
 }
 
@@ -695,6 +746,18 @@ extern "C" int pmfb_pointwise(const pmfb_view* in, float* out, int64_t o_sn, int
 extern "C" int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n,
                                 int32_t h, int32_t w, int32_t c, const pmfb_epilogue* epi, void* out16, int32_t dtype16,
                                 void* out16_bf16, int32_t in_half, void* stream) {
+  return pmfb_pointwise16_bn(in, out, o_sn, o_sy, o_sx, n, h, w, c, epi, out16, dtype16, out16_bf16, in_half, nullptr, stream);
+}
+
+extern "C" int pmfb_pointwise16_bn(const pmfb_view* in, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t n,
+                                   int32_t h, int32_t w, int32_t c, const pmfb_epilogue* epi, void* out16, int32_t dtype16,
+                                   void* out16_bf16, int32_t in_half, const pmfb_bn_fuse* bn, void* stream) {
+  REQ(!bn || (in_half && bn->sums && bn->count > 0 && bn->alpha_out && bn->beta_out && bn->mean_out && bn->invstd_out && epi &&
+              !epi->alpha1 && !epi->beta1),
+      "pointwise16_bn: the fused finalisation needs in_half, sums, count > 0, the four output vectors and NULL alpha1 / beta1");
+  REQ(!bn || ((reinterpret_cast<uintptr_t>(bn->alpha_out) | reinterpret_cast<uintptr_t>(bn->beta_out) |
+               reinterpret_cast<uintptr_t>(bn->mean_out) | reinterpret_cast<uintptr_t>(bn->invstd_out)) & 15) == 0,
+      "pointwise16_bn: output vectors must be 16-byte aligned");
   REQ(!in_half || (in && in->ptr), "pointwise16: in_half needs an input view");
   REQ(!out16_bf16 || (reinterpret_cast<uintptr_t>(out16_bf16) & 7) == 0, "pointwise16: the bf16 output must be 8-byte aligned");
   REQ(epi && c > 0 && c % 4 == 0, "pointwise: c=%d must be a positive multiple of 4", c);
@@ -709,6 +772,7 @@ extern "C" int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, i
   if (npix == 0) return PMFB_OK;
   REQ(npix < (1ll << 31), "pointwise: too many pixels");
   PWParams P;
+  P.bn = pmfb_bn_fuse{};
   P.in = in ? pwv(in->ptr, in->sn, in->sy, in->sx, h, w) : pwv(nullptr, 0, 0, 0, h, w);
   P.out = pwv(out, o_sn, o_sy, o_sx, h, w);
   P.r1 = pwv(E.r1.p, E.r1.sn, E.r1.sy, E.r1.sx, h, w);
@@ -727,6 +791,15 @@ extern "C" int pmfb_pointwise16(const pmfb_view* in, float* out, int64_t o_sn, i
   const cudaStream_t st = (cudaStream_t)stream;
   REQ(!in_half || (P.in.linear && P.out.linear && (!P.r1.p || P.r1.linear) && (!P.r2.p || P.r2.linear)),
       "pointwise16: in_half needs dense (pixel-linear) in / out / r1 / r2 views");
+  if (bn) {
+    P.bn = *bn;
+#define PMFB_PWB(o) case o: return launch_pointwise_t<o, true, true>(P, npix, h, w, c / 4, st);
+    switch (ops) {
+      PMFB_PWB(0) PMFB_PWB(1) PMFB_PWB(2) PMFB_PWB(3) PMFB_PWB(4) PMFB_PWB(5) PMFB_PWB(6)
+      default: return launch_pointwise_t<7, true, true>(P, npix, h, w, c / 4, st);
+    }
+#undef PMFB_PWB
+  }
 #define PMFB_PW(o) case o: return in_half ? launch_pointwise_t<o, true>(P, npix, h, w, c / 4, st) : launch_pointwise_t<o, false>(P, npix, h, w, c / 4, st);
   switch (ops) {
     PMFB_PW(0) PMFB_PW(1) PMFB_PW(2) PMFB_PW(3) PMFB_PW(4) PMFB_PW(5) PMFB_PW(6)
@@ -754,7 +827,7 @@ extern "C" int pmfb_nhwc_to_nchw(const pmfb_view* src, int32_t n, int32_t h, int
   REQ(src && src->ptr && dst && c > 0, "nhwc_to_nchw: bad arguments");
   const long long tiles = (long long)n * (((long long)h * w + 31) / 32) * ((c + 31) / 32);
   if (tiles == 0) return PMFB_OK;
-  nhwc_to_nchw_kernel<<<(int)(tiles < 148 * 16 ? tiles : 148 * 16), 256, 0, (cudaStream_t)stream>>>(ev(src), n, h, w, c, dst);
+  nhwc_to_nchw_kernel<<<(int)(tiles < sm_count() * 16 ? tiles : sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(ev(src), n, h, w, c, dst);
   PMFB_LAUNCH_CHECK("nhwc_to_nchw_kernel");
   return PMFB_OK;
 }
@@ -1092,13 +1165,15 @@ extern "C" int pmfb_d2f(const double* src, float* dst, int64_t n, float scale, i
 
 extern "C" int pmfb_pool3s2(int32_t kind, const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c,
                             const float* chan_scale, float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, uint8_t* idx,
-                            int32_t round_out, void* stream) {
+                            int32_t round_out, void* out16, void* out16_bf16, void* stream) {
   REQ(x && x->ptr && view_ok(x) && out_ok(out, o_sn, o_sy, o_sx), "pool3s2: bad views");
+  REQ(((reinterpret_cast<uintptr_t>(out16) | reinterpret_cast<uintptr_t>(out16_bf16)) & 7) == 0, "pool3s2: 16-bit outputs must be 8-byte aligned");
   REQ(c % 4 == 0 && h % 2 == 0 && w % 2 == 0 && (kind == 0 || kind == 1), "pool3s2: c%%4, even h/w, kind in {0,1}");
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 4);
   if (total == 0) return PMFB_OK;
   pool3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(kind, ev(x), n, h, w, c / 4, chan_scale, out, o_sn, o_sy,
-                                                                         o_sx, idx, round_out);
+                                                                         o_sx, idx, round_out, static_cast<unsigned short*>(out16),
+                                                                         static_cast<unsigned short*>(out16_bf16));
   PMFB_LAUNCH_CHECK("pool3s2_kernel");
   return PMFB_OK;
 }
@@ -1118,12 +1193,15 @@ extern "C" int pmfb_pool3s2_bwd(int32_t kind, const pmfb_view* dy, int32_t n, in
 }
 
 extern "C" int pmfb_pixel_shuffle(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, const float* chan_scale,
-                                  float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t round_out, void* stream) {
+                                  float* out, int64_t o_sn, int64_t o_sy, int64_t o_sx, int32_t round_out, void* out16,
+                                  void* out16_bf16, void* stream) {
   REQ(x && x->ptr && view_ok(x) && out_ok(out, o_sn, o_sy, o_sx) && c % 4 == 0, "pixel_shuffle: bad arguments");
+  REQ(((reinterpret_cast<uintptr_t>(out16) | reinterpret_cast<uintptr_t>(out16_bf16)) & 7) == 0, "pixel_shuffle: 16-bit outputs must be 8-byte aligned");
   const long long total = (long long)n * h * w * (c / 4);
   if (total == 0) return PMFB_OK;
   pixel_shuffle_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(x), n, h, w, c / 4, chan_scale, out, o_sn, o_sy,
-                                                                               o_sx, round_out);
+                                                                               o_sx, round_out, static_cast<unsigned short*>(out16),
+                                                                               static_cast<unsigned short*>(out16_bf16));
   PMFB_LAUNCH_CHECK("pixel_shuffle_kernel");
   return PMFB_OK;
 }
@@ -1141,11 +1219,13 @@ extern "C" int pmfb_pixel_shuffle_bwd(const pmfb_view* dy, int32_t n, int32_t h,
 }
 
 extern "C" int pmfb_upsample2x(const pmfb_view* x, int32_t n, int32_t h, int32_t w, int32_t c, float* out, int64_t o_sn,
-                               int64_t o_sy, int64_t o_sx, int32_t round_out, void* stream) {
+                               int64_t o_sy, int64_t o_sx, int32_t round_out, void* out16, void* out16_bf16, void* stream) {
   REQ(x && x->ptr && view_ok(x) && out_ok(out, o_sn, o_sy, o_sx) && c % 4 == 0, "upsample2x: bad arguments");
+  REQ(((reinterpret_cast<uintptr_t>(out16) | reinterpret_cast<uintptr_t>(out16_bf16)) & 7) == 0, "upsample2x: 16-bit outputs must be 8-byte aligned");
   const long long total = (long long)n * (2 * h) * (2 * w) * (c / 4);
   if (total == 0) return PMFB_OK;
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(x), n, h, w, c / 4, out, o_sn, o_sy, o_sx,
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(ev(x), n, h, w, c / 4, static_cast<unsigned short*>(out16),
+                                                                            static_cast<unsigned short*>(out16_bf16), out, o_sn, o_sy, o_sx,
                                                                             round_out);
   PMFB_LAUNCH_CHECK("upsample2x_kernel");
   return PMFB_OK;

@@ -23,7 +23,7 @@ namespace pmfb {
 static inline int lgrid(long long work, int threads, int per_sm = 8) {
   long long b = (work + threads - 1) / threads;
   if (b < 1) b = 1;
-  const long long cap = 148LL * per_sm;
+  const long long cap = (long long)sm_count() * per_sm;
   return (int)(b > cap ? cap : b);
 }
 

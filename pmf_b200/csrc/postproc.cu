@@ -378,7 +378,7 @@ extern "C" int pmfb_knn_vote(const float* proj_range, const int64_t* proj_argmax
   REQ(unproj_range && px && py && out && n_points > 0, "knn_vote: bad point arrays");
   if (knn <= kKnnRegK) {  // thread-per-point kernel (top-k in registers); the warp kernel keeps k > 8
     long long tb = (n_points + 127) / 128;
-    if (tb > 148 * 16) tb = 148 * 16;
+    if (tb > sm_count() * 16) tb = sm_count() * 16;
     knn_vote_points_kernel<kKnnRegK><<<(int)tb, 128, 0, (cudaStream_t)stream>>>(
         proj_range, reinterpret_cast<const long long*>(proj_argmax), 1, h, w, unproj_range, reinterpret_cast<const long long*>(px),
         reinterpret_cast<const long long*>(py), nullptr, n_points, inv_gauss, search, knn, cutoff, nclasses,
@@ -387,7 +387,7 @@ extern "C" int pmfb_knn_vote(const float* proj_range, const int64_t* proj_argmax
     return PMFB_OK;
   }
   long long blocks = (n_points + 7) / 8;  // 8 warps per CTA, one point per warp per iteration
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks > sm_count() * 32) blocks = sm_count() * 32;
   knn_vote_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
       proj_range, reinterpret_cast<const long long*>(proj_argmax), h, w, unproj_range, reinterpret_cast<const long long*>(px),
       reinterpret_cast<const long long*>(py), n_points, inv_gauss, search, knn, cutoff, nclasses,
@@ -408,7 +408,7 @@ extern "C" int pmfb_knn_vote_batched(const float* proj_range, const int64_t* pro
   if (n_points == 0) return PMFB_OK;
   REQ(unproj_range && px && py && out && n_points > 0, "knn_vote_batched: bad point arrays");
   long long tb = (n_points + 127) / 128;
-  if (tb > 148 * 16) tb = 148 * 16;
+  if (tb > sm_count() * 16) tb = sm_count() * 16;
   knn_vote_points_kernel<kKnnRegK><<<(int)tb, 128, 0, (cudaStream_t)stream>>>(
       proj_range, reinterpret_cast<const long long*>(proj_argmax), n_frames, h, w, unproj_range, reinterpret_cast<const long long*>(px),
       reinterpret_cast<const long long*>(py), reinterpret_cast<const long long*>(point_offsets), n_points, inv_gauss, search, knn,
@@ -423,7 +423,7 @@ extern "C" int pmfb_argmax_nchw(const float* probs, int32_t n, int32_t c, int32_
   REQ(y0 >= 0 && x0 >= 0 && out_h > 0 && out_w > 0 && y0 + out_h <= h && x0 + out_w <= w, "argmax_nchw: crop window outside the map");
   const long long total = (long long)n * out_h * out_w;
   long long b = (total + 255) / 256;
-  if (b > 148 * 16) b = 148 * 16;
+  if (b > sm_count() * 16) b = sm_count() * 16;
   argmax_nchw_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(probs, n, c, h, w, y0, x0, out_h, out_w,
                                                               reinterpret_cast<long long*>(label), conf);
   PMFB_LAUNCH_CHECK("argmax_nchw_kernel");
@@ -435,7 +435,7 @@ extern "C" int pmfb_lut_remap(const int64_t* labels, int64_t n, const int32_t* l
   if (n == 0) return PMFB_OK;
   REQ(labels && out, "lut_remap: null arrays");
   long long b = (n + 255) / 256;
-  if (b > 148 * 8) b = 148 * 8;
+  if (b > sm_count() * 8) b = sm_count() * 8;
   lut_remap_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(labels), n, lut, lut_size, out);
   PMFB_LAUNCH_CHECK("lut_remap_kernel");
   return PMFB_OK;
@@ -451,13 +451,13 @@ extern "C" int pmfb_merge_cameras(const int64_t* point_idx, const float* conf, c
   if (n_entries > 0) {
     REQ(point_idx && conf && argmax && cam, "merge_cameras: null inputs");
     long long b = (n_entries + 255) / 256;
-    if (b > 148 * 8) b = 148 * 8;
+    if (b > sm_count() * 8) b = sm_count() * 8;
     merge_cameras_pass1<<<(int)b, 256, 0, st>>>(reinterpret_cast<const long long*>(point_idx), conf, cam, n_entries, pc_size,
                                                reinterpret_cast<unsigned long long*>(scratch));
     PMFB_LAUNCH_CHECK("merge_cameras_pass1");
   }
   long long b2 = (pc_size + 255) / 256;
-  if (b2 > 148 * 8) b2 = 148 * 8;
+  if (b2 > sm_count() * 8) b2 = sm_count() * 8;
   merge_cameras_pass2<<<(int)b2, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(scratch),
                                               reinterpret_cast<const long long*>(argmax), pc_size,
                                               reinterpret_cast<long long*>(merged));
@@ -471,7 +471,7 @@ extern "C" int pmfb_confusion_add(const int64_t* pred, const int64_t* target, in
   if (n == 0) return PMFB_OK;
   REQ(pred && target, "confusion_add: null inputs");
   long long b = (n + 255) / 256;
-  if (b > 148 * 4) b = 148 * 4;
+  if (b > sm_count() * 4) b = sm_count() * 4;
   confusion_add_kernel<<<(int)b, 256, (size_t)nclasses * nclasses * 4, (cudaStream_t)stream>>>(
       reinterpret_cast<const long long*>(pred), reinterpret_cast<const long long*>(target), n, nclasses,
       reinterpret_cast<unsigned long long*>(conf));
@@ -489,11 +489,11 @@ extern "C" int pmfb_project_scatter(const float* points, const int32_t* labels, 
   for (int i = 0; i < 12; ++i) M.m[i] = proj_matrix[i];  // host pointer: 3x4 row-major float64 (P2 @ Tr)
   cudaStream_t st = (cudaStream_t)stream;
   const long long hw = (long long)h * w;
-  int blocks = (int)((hw + 255) / 256 < 148 * 8 ? (hw + 255) / 256 : 148 * 8);
+  int blocks = (int)((hw + 255) / 256 < sm_count() * 8 ? (hw + 255) / 256 : sm_count() * 8);
   fill_i32_kernel<<<blocks, 256, 0, st>>>(winner, hw, -1);
   PMFB_LAUNCH_CHECK("fill_i32_kernel");
   if (n_points > 0) {
-    int pb = (int)((n_points + 255) / 256 < 148 * 8 ? (n_points + 255) / 256 : 148 * 8);
+    int pb = (int)((n_points + 255) / 256 < sm_count() * 8 ? (n_points + 255) / 256 : sm_count() * 8);
     project_points_kernel<<<pb, 256, 0, st>>>(points, n_points, M, h, w, winner, rows, cols, depth);
     PMFB_LAUNCH_CHECK("project_points_kernel");
   }

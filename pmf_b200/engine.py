@@ -18,7 +18,7 @@ import os
 import torch
 
 from . import _lib as L
-from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ConvDesc, Epilogue, TmaSrc, View, WeightJob, WgradDesc
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, BnFuse, ConvDesc, Epilogue, TmaSrc, View, WeightJob, WgradDesc
 
 BN_EPS_DEFAULT = 1e-5
 # forward / dgrad: 16-bit operands from one full 64-channel slab on.  (32-channel layers CAN run on 64-byte operand rows,
@@ -30,7 +30,8 @@ H16_WGRAD = os.environ.get("PMFB_H16_WGRAD", "1") != "0"
 # "f16" mode: the pre-BatchNorm activation of a training-mode conv -> [LeakyReLU] -> BN layer is STORED as fp16 by the conv
 # epilogue (pmfb_conv_desc.out_half); only the BatchNorm passes read it (apply, backward reduce, backward apply)
 PRE_BN_HALF = os.environ.get("PMFB_PRE_BN_HALF", "1") != "0"
-N_SM = 148
+# ... and the BatchNorm finalisation of such a layer runs inside its BN-apply launch (pmfb_pointwise16_bn)
+BN_FUSE_FINALIZE = os.environ.get("PMFB_BN_FUSE_FINALIZE", "1") != "0"
 
 
 def _rup(x, m):
@@ -449,6 +450,7 @@ class Engine:
         self.cache.precise = self.precise
         self.cache.begin_pass()
         self.st = torch.cuda.current_stream(device).cuda_stream
+        self.n_sm = L.query("pmfb_sm_count")
         if self.cache.always and self.cache.table is not None:
             self.cache.pack_all(self.st)
         self._wg_list = []       # recorded convs in forward order (backward: one arena, one memset, one unpack launch)
@@ -486,6 +488,21 @@ class Engine:
                 a.hb = torch.empty((n, h, w, c), device=self.device, dtype=torch.bfloat16)
         return a
 
+    def _shadow_ptrs(self, out):
+        """(fp16 ptr, bf16 ptr) of the shadows of Act ``out`` for a producer that writes them in its own pass (marks them
+        valid); (None, None) outside "f16" mode or when the buffer has no shadows."""
+        if not self.h16:
+            return None, None
+        sh, shb = out.shadow(), out.shadow(True)
+        for t in (sh, shb):
+            if t is not None:
+                assert tuple(t.stride()) == tuple(out.t.stride()), (t.stride(), out.t.stride())
+        if sh is not None:
+            out.shadow_mark()
+        if shb is not None:
+            out.shadow_mark(True)
+        return _p(sh), _p(shb)
+
     def _ensure_shadow(self, x, bf16=False):
         """fp16 (bf16) shadow view of Act x with current values (converted here if its producer did not write it), or
         None when the buffer has no such shadow."""
@@ -509,26 +526,30 @@ class Engine:
         e.act, e.round_out = act, (rnd if self.R else 0)
         return e
 
-    def pointwise(self, src, dst, shadow=None, **kw):
+    def pointwise(self, src, dst, shadow=None, bn_fuse=None, **kw):
         """dst = epilogue(src) elementwise; src None means zeros; src may be a View (broadcast).  ``shadow``: the Act that
-        owns ``dst``; in "f16" mode its fp16 shadow is written by the same pass."""
+        owns ``dst``; in "f16" mode its fp16 shadow is written by the same pass.  ``bn_fuse``: a BnFuse whose finalisation
+        (alpha1 / beta1 from the fused channel sums) runs inside this launch (src is then the fp16 pre-BN activation)."""
         n, h, w, c = dst.shape
         e = self._epi(**kw)
         sv = src if isinstance(src, View) else _view(src)
         in_half = 1 if (torch.is_tensor(src) and src.dtype == torch.float16) else 0
         sh = shadow.shadow() if (self.h16 and shadow is not None) else None
+        shb = None
         if sh is not None:
             assert tuple(sh.stride()) == tuple(dst.stride()), (sh.stride(), dst.stride())
             shb = shadow.shadow(True)
-            L.call("pmfb_pointwise16", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
-                   C.byref(e), sh.data_ptr(), L.DT_F16, _p(shb), in_half, self.st)
             shadow.shadow_mark()
             if shb is not None:
                 shadow.shadow_mark(True)
+        if bn_fuse is not None:
+            assert in_half
+            L.call("pmfb_pointwise16_bn", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
+                   C.byref(e), _p(sh), L.DT_F16, _p(shb), 1, C.byref(bn_fuse), self.st)
             return
-        if in_half:
+        if sh is not None or in_half:
             L.call("pmfb_pointwise16", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
-                   C.byref(e), None, L.DT_F16, None, 1, self.st)
+                   C.byref(e), _p(sh), L.DT_F16, _p(shb), in_half, self.st)
             return
         L.call("pmfb_pointwise", C.byref(sv), dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), n, h, w, c,
                C.byref(e), self.st)
@@ -756,7 +777,7 @@ class Engine:
         d.n_tile = min(256, _rup(cp.c_out_p, 32))
         total_pt = (_rup(ow, d.ptile_w) // d.ptile_w) * (_rup(oh, d.ptile_h) // d.ptile_h) * n
         base = ((cp.taps * (_rup(cp.c_in_p, 32) // 32) + 3) // 4) * ((cp.c_out_p + d.n_tile - 1) // d.n_tile)
-        d.ksplit = max(1, min(max(1, total_pt // 4), (2 * N_SM + base - 1) // base))
+        d.ksplit = max(1, min(max(1, total_pt // 4), (2 * self.n_sm + base - 1) // base))
         d.dw = packed.data_ptr()
         main_st = self.st
         if self.use_side:
@@ -850,19 +871,35 @@ class Engine:
         return alpha, beta
 
     def _conv_fwd_with_stats(self, x, cp, bn, shp, epi):
-        """(a, stats): a = epi(conv(x)), the pre-BatchNorm activation, and the training-mode BatchNorm statistics of it --
-        fused into the conv's epilogue where the library supports it (pmfb_conv_fused_stats_ok), else by a separate
+        """(a, stats, fuse): a = epi(conv(x)), the pre-BatchNorm activation, and the training-mode BatchNorm statistics of it
+        -- fused into the conv's epilogue where the library supports it (pmfb_conv_fused_stats_ok), else by a separate
         pmfb_bn_stats pass.  "f16" mode: a is stored as fp16 where the fused epilogue exists (statistics of the stored
-        values); the three BatchNorm passes that read it take fp16."""
+        values); the three BatchNorm passes that read it take fp16, and the finalisation (sums -> alpha / beta / mean /
+        invstd, running statistics) is deferred into the BN-apply launch: ``fuse`` is then the BnFuse the caller hands to
+        ``pointwise`` -- stats' vectors are filled by that launch -- and alpha1 / beta1 must not be passed."""
         assert cp.c_out_p == bn.c
         sums = self.d64.take(2 * bn.c)
         if self.h16 and PRE_BN_HALF and shp[3] % 8 == 0:
             a = torch.empty(shp, device=self.device, dtype=torch.float16)
             if self._conv_fwd(x, cp, a, epi, bn_stats=sums, out_half=True):
-                return a, self._bn_train_affine(bn, a, sums=sums, have_sums=True)
+                if not BN_FUSE_FINALIZE:
+                    return a, self._bn_train_affine(bn, a, sums=sums, have_sums=True), None
+                c = bn.c
+                v = self.f32.take(4 * c)
+                stats = (v[:c], v[c:2 * c], v[2 * c:3 * c], v[3 * c:])
+                f = BnFuse()
+                f.sums, f.count = sums.data_ptr(), shp[0] * shp[1] * shp[2]
+                f.gamma, f.beta = _p(bn.weight.detach()), _p(bn.bias.detach())
+                f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+                f.momentum, f.eps = bn.momentum, bn.eps
+                f.alpha_out, f.beta_out, f.mean_out, f.invstd_out = (t.data_ptr() for t in stats)
+                f._keep = (sums, v, bn)
+                if bn.nbt is not None:
+                    self.nbt_list.append(bn.nbt)
+                return a, stats, f
         a = torch.empty(shp, device=self.device, dtype=torch.float32)
         fused = self._conv_fwd(x, cp, a, epi, bn_stats=sums)
-        return a, self._bn_train_affine(bn, a, sums=sums, have_sums=fused)
+        return a, self._bn_train_affine(bn, a, sums=sums, have_sums=fused), None
 
     def _bn_train_affine(self, bn, a_t, sums=None, have_sums=False):
         n, h, w, c = a_t.shape
@@ -972,9 +1009,10 @@ class Engine:
             alpha, beta = self._bn_eval_affine(bn)
             self._conv_fwd(x, cp, y.t, self._epi(beta1=e["bias"], act=ACT_LEAKY, alpha2=alpha, beta2=beta, r2=sc_t, rnd=1))
             return y
-        a, stats = self._conv_fwd_with_stats(x, cp, bn, shp, self._epi(beta1=e["bias"], act=ACT_LEAKY))
+        a, stats, fuse = self._conv_fwd_with_stats(x, cp, bn, shp, self._epi(beta1=e["bias"], act=ACT_LEAKY))
         mv = None if mask is None else _chan_view(mask)
-        self.pointwise(a, y.t, shadow=y, alpha1=stats[0], beta1=stats[1], r1=sc_t, mul=mv, rnd=1)
+        ab = {} if fuse is not None else dict(alpha1=stats[0], beta1=stats[1])
+        self.pointwise(a, y.t, shadow=y, bn_fuse=fuse, r1=sc_t, mul=mv, rnd=1, **ab)
         if self.record:
             def bwd():
                 dy = y.grad_read()
@@ -1015,10 +1053,11 @@ class Engine:
             self._conv_fwd(x, cp, y.t, self._epi(alpha1=alpha, beta1=beta, r1=id_t, act=post, mul=f_t, r2=pcd_t,
                                                  rnd=1 if rnd else 0))
             return y
-        c_t, stats = self._conv_fwd_with_stats(x, cp, bn, shp, self._epi(beta1=e["bias"]))
+        c_t, stats, fuse = self._conv_fwd_with_stats(x, cp, bn, shp, self._epi(beta1=e["bias"]))
         mv = None if mask is None else _chan_view(mask)
-        self.pointwise(c_t, y.t, shadow=y if rnd else None, alpha1=stats[0], beta1=stats[1], r1=id_t, act=post,
-                       mul=f_t if gate is not None else mv, r2=pcd_t, rnd=1 if rnd else 0)
+        ab = {} if fuse is not None else dict(alpha1=stats[0], beta1=stats[1])
+        self.pointwise(c_t, y.t, shadow=y if rnd else None, bn_fuse=fuse, r1=id_t, act=post,
+                       mul=f_t if gate is not None else mv, r2=pcd_t, rnd=1 if rnd else 0, **ab)
         if self.record:
             def bwd():
                 dy = y.grad_read()
@@ -1125,8 +1164,9 @@ class Engine:
         if out is None:
             out = self.new(n, h // 2, w // 2, c)
         idx = torch.empty((n, h // 2, w // 2, c), device=self.device, dtype=torch.uint8) if (k == 1 and self.record) else None
+        s16, s16b = self._shadow_ptrs(out)
         L.call("pmfb_pool3s2", k, C.byref(_view(x.t)), n, h, w, c, _p(mask), out.t.data_ptr(), out.t.stride(0), out.t.stride(1),
-               out.t.stride(2), _p(idx), self.R, self.st)
+               out.t.stride(2), _p(idx), self.R, s16, s16b, self.st)
         if self.record and x.needs_grad:
             def bwd():
                 g = out.grad_read()
@@ -1141,8 +1181,9 @@ class Engine:
         """nn.PixelShuffle(2) (+ Dropout2d scale): out (N,2h,2w,c/4)."""
         n, h, w, c4 = x.shape
         c = c4 // 4
+        s16, s16b = self._shadow_ptrs(out)
         L.call("pmfb_pixel_shuffle", C.byref(_view(x.t)), n, h, w, c, _p(mask), out.t.data_ptr(), out.t.stride(0),
-               out.t.stride(1), out.t.stride(2), self.R, self.st)
+               out.t.stride(1), out.t.stride(2), self.R, s16, s16b, self.st)
         if self.record and x.needs_grad:
             def bwd():
                 g = out.grad_read()
@@ -1155,8 +1196,9 @@ class Engine:
 
     def upsample2x(self, x, out):
         n, h, w, c = x.shape
+        s16, s16b = self._shadow_ptrs(out)
         L.call("pmfb_upsample2x", C.byref(_view(x.t)), n, h, w, c, out.t.data_ptr(), out.t.stride(0), out.t.stride(1),
-               out.t.stride(2), self.R, self.st)
+               out.t.stride(2), self.R, s16, s16b, self.st)
         if self.record and x.needs_grad:
             def bwd():
                 g = out.grad_read()

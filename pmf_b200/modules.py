@@ -286,6 +286,17 @@ class _PMFFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
+GRAPH_CACHE = max(1, int(os.environ.get("PMFB_GRAPH_CACHE", "8")))
+
+
+def _evict_lru(graphs):
+    """Captured specialisations (train / eval x input shape x parameter storage) are kept least-recently-used first: a
+    trainer alternating a train and a validation shape keeps both graphs; only the oldest entry goes when the cache
+    (PMFB_GRAPH_CACHE, default 8) is full."""
+    while len(graphs) >= GRAPH_CACHE:
+        graphs.pop(next(iter(graphs)))
+
+
 class _GraphedPMF:
     """One (shape, mode, parameter-storage) specialisation of PMFNet captured into CUDA graphs.
 
@@ -543,12 +554,12 @@ class PMFNet(nn.Module):
             key = self._graph_key(pcd_feature, img_feature, record, params)
             runner = self._graphs.get(key)
             if runner is None and key in self._seen:  # second call with this specialisation: capture it
-                if len(self._graphs) >= 4:
-                    self._graphs.clear()
+                _evict_lru(self._graphs)
                 torch.cuda.empty_cache()
                 runner = self._graphs[key] = _GraphedPMF(self, pcd_feature, img_feature, record)
             self._seen.add(key)
             if runner is not None:
+                self._graphs[key] = self._graphs.pop(key)  # most recently used last
                 return _graph_apply(runner, pcd_feature, img_feature, dict(self.named_parameters()))
         return _PMFFn.apply(self, record, pcd_feature, img_feature, *params)
 
@@ -711,12 +722,12 @@ class EPMFNet(nn.Module):
                    tuple(p.data_ptr() for p in self.parameters()) + tuple(b.data_ptr() for b in self.buffers()))
             runner = self._graphs.get(key)
             if runner is None and key in self._seen:
-                if len(self._graphs) >= 4:
-                    self._graphs.clear()
+                _evict_lru(self._graphs)
                 torch.cuda.empty_cache()
                 runner = self._graphs[key] = _GraphedEPMF(self, pcd_feature, img_feature)
             self._seen.add(key)
             if runner is not None:
+                self._graphs[key] = self._graphs.pop(key)  # most recently used last
                 return runner.forward(pcd_feature, img_feature)
         E = Engine(G.ModuleParams(self), pcd_feature.device, False, False, self._cache, dropout=False)
         lidar, camera, _, _ = G.epmf_forward(E, pcd_feature, img_feature, self.image_backbone, self.nclasses)

@@ -271,7 +271,8 @@ def pmfb_bn_bwd_apply(dy, mul, z, act_z, x, mean, invstd, alpha, beta, gamma, re
         _vec(colsum, c, np.float64)[...] += d.astype(np.float64).sum((0, 1, 2))
 
 
-def pmfb_pool3s2(kind, x, n, h, w, c, chan_scale, out, o_sn, o_sy, o_sx, idx, rnd, stream):
+def pmfb_pool3s2(kind, x, n, h, w, c, chan_scale, out, o_sn, o_sy, o_sx, idx, rnd, out16, out16b, stream):
+    assert not out16 and not out16b
     v = np.array(_view(_deref(x), n, h, w, c))
     ho, wo = h // 2, w // 2
     pad = np.full((n, h + 2, w + 2, c), 0.0 if kind == 0 else -np.inf, np.float32)
@@ -305,7 +306,8 @@ def pmfb_pool3s2_bwd(kind, dy, n, h, w, c, chan_scale, dx, d_sn, d_sy, d_sx, idx
     o[...] = o + res if accumulate else res
 
 
-def pmfb_pixel_shuffle(x, n, h, w, c, chan_scale, out, o_sn, o_sy, o_sx, rnd, stream):
+def pmfb_pixel_shuffle(x, n, h, w, c, chan_scale, out, o_sn, o_sy, o_sx, rnd, out16, out16b, stream):
+    assert not out16 and not out16b
     v = np.array(_view(_deref(x), n, h, w, 4 * c)).reshape(n, h, w, c, 2, 2)
     res = np.transpose(v, (0, 1, 4, 2, 5, 3)).reshape(n, 2 * h, 2 * w, c)
     if chan_scale:
@@ -335,7 +337,8 @@ def _up_matrix(size):
     return m
 
 
-def pmfb_upsample2x(x, n, h, w, c, out, o_sn, o_sy, o_sx, rnd, stream):
+def pmfb_upsample2x(x, n, h, w, c, out, o_sn, o_sy, o_sx, rnd, out16, out16b, stream):
+    assert not out16 and not out16b
     v = np.array(_view(_deref(x), n, h, w, c))
     res = np.einsum("ah,nhwc->nawc", _up_matrix(h), v)
     res = np.einsum("bw,nawc->nabc", _up_matrix(w), res).astype(np.float32)
@@ -437,6 +440,10 @@ def pmfb_conv_fwd(dp_, stream):
         v = res.astype(np.float64)
         st[:d.c_out] += v.sum((0, 1, 2))
         st[d.c_out:] += (v * v).sum((0, 1, 2))
+
+
+def pmfb_sm_count():
+    return 148
 
 
 def pmfb_conv_fused_stats_ok(dp_):

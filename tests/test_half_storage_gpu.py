@@ -140,3 +140,47 @@ def test_conv_fp16_output_with_fused_statistics(dev, geom):
     st = y16.double()
     assert torch.allclose(s16[:co], st.sum((0, 1, 2)), rtol=1e-6, atol=1e-4)
     assert torch.allclose(s16[co:], (st * st).sum((0, 1, 2)), rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 40, 32), (3, 17, 23, 64), (1, 9, 11, 8), (2, 30, 40, 256)])
+def test_fused_bn_finalisation_equals_the_separate_launch(dev, shape):
+    """pmfb_pointwise16_bn (finalisation inside the BN-apply launch) == pmfb_bn_finalize followed by pmfb_pointwise16, bit
+    for bit: outputs, alpha / beta / mean / invstd and the running statistics."""
+    from pmf_b200 import _lib as L
+    from pmf_b200._lib import BnFuse, Epilogue
+    from pmf_b200.engine import _view
+    n, h, w, c = shape
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cpu").manual_seed(sum(shape))
+    a16 = (torch.randn(n, h, w, c, generator=g) * 2 + 0.3).half().to(dev)
+    ad = a16.double()
+    sums = torch.cat([ad.sum((0, 1, 2)), (ad * ad).sum((0, 1, 2))]).contiguous()
+    gamma = (torch.rand(c, generator=g) + 0.5).to(dev)
+    beta = torch.randn(c, generator=g).to(dev)
+    shortcut = torch.randn(n, h, w, c, generator=g).to(dev)
+    res = []
+    for fused in (False, True):
+        rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+        v = torch.empty(4 * c, device=dev)
+        alpha, bt, mean, invstd = (v[i * c:(i + 1) * c] for i in range(4))
+        y = torch.empty(n, h, w, c, device=dev)
+        y16 = torch.empty(n, h, w, c, device=dev, dtype=torch.float16)
+        e = Epilogue()
+        e.r1, e.round_out = _view(shortcut), 1
+        if fused:
+            f = BnFuse()
+            f.sums, f.count, f.gamma, f.beta = sums.data_ptr(), n * h * w, gamma.data_ptr(), beta.data_ptr()
+            f.running_mean, f.running_var, f.momentum, f.eps = rm.data_ptr(), rv.data_ptr(), 0.1, 1e-5
+            f.alpha_out, f.beta_out, f.mean_out, f.invstd_out = alpha.data_ptr(), bt.data_ptr(), mean.data_ptr(), invstd.data_ptr()
+            L.call("pmfb_pointwise16_bn", C.byref(_view(a16)), y.data_ptr(), c * h * w, c * w, c, n, h, w, c, C.byref(e),
+                   y16.data_ptr(), L.DT_F16, None, 1, C.byref(f), st)
+        else:
+            L.call("pmfb_bn_finalize", sums.data_ptr(), n * h * w, c, gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                   0.1, 1e-5, alpha.data_ptr(), bt.data_ptr(), mean.data_ptr(), invstd.data_ptr(), st)
+            e.alpha1, e.beta1 = alpha.data_ptr(), bt.data_ptr()
+            L.call("pmfb_pointwise16", C.byref(_view(a16)), y.data_ptr(), c * h * w, c * w, c, n, h, w, c, C.byref(e),
+                   y16.data_ptr(), L.DT_F16, None, 1, st)
+        torch.cuda.synchronize()
+        res.append((y, y16, v, rm, rv))
+    for t0, t1 in zip(*res):
+        assert torch.equal(t0, t1)
