@@ -379,59 +379,80 @@ pool3s2_kernel(int kind, EpiView xin, int n, int h, int w, int c4, const float* 
 
 // gather form: every input pixel sums the (at most 4) output windows that cover it.  32-bit index arithmetic and all
 // four candidate loads (plus the accumulate read) issued before the first use: the kernel is a pure HBM stream.
-__global__ void __launch_bounds__(256)
-pool3s2_bwd_kernel(int kind, EpiView dy, int n, int h, int w, int c4, const float* __restrict__ chan_scale, float* dx,
+template <int KIND>
+__global__ void __launch_bounds__(256, 3)
+pool3s2_bwd_kernel(EpiView dy, int n, int h, int w, int c4, const float* __restrict__ chan_scale, float* dx,
                    long long d_sn, long long d_sy, long long d_sx, const uint8_t* __restrict__ idx, int accumulate) {
+  // Two (pixel, 4-channel group) items per thread and trip, every load of both issued before the first use: the kernel is a
+  // gather (<= 4 pooled gradients per pixel, mostly L2 hits) plus one full-resolution read-modify-write stream, and with one
+  // item per trip it ran latency-bound at 1.9 TB/s.
+  constexpr int U = KIND == 0 ? 2 : 1;
   const unsigned ho = h / 2, wo = w / 2;
   const unsigned total = (unsigned)n * h * w * c4;  // host guarantees < 2^32
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const unsigned cg = i % (unsigned)c4;
-    unsigned p = i / (unsigned)c4;
-    const unsigned x = p % (unsigned)w;
-    p /= (unsigned)w;
-    const unsigned y = p % (unsigned)h;
-    const unsigned ni = p / (unsigned)h;
-    const int c = cg * 4;
-    // windows: 2*yo-1 <= y <= 2*yo+1  ->  yo in {y/2, (y+1)/2}
-    const unsigned yo[2] = {y / 2, (y + 1) / 2}, xo[2] = {x / 2, (x + 1) / 2};
-    const bool vy[2] = {true, (y & 1u) && yo[1] < ho}, vx[2] = {true, (x & 1u) && xo[1] < wo};
-    float4 g[4];
-    uchar4 am[4];
+  const unsigned step = gridDim.x * blockDim.x;
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * step) {
+    float4 g[U][4], old[U], sc[U];
+    uchar4 am[KIND != 0 ? U : 1][4];
+    unsigned tk[KIND != 0 ? U : 1][4];
+    float* dptr[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int a = k >> 1, b = k & 1;
-      g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      am[k] = make_uchar4(255, 255, 255, 255);
-      if (vy[a] && vx[b]) {
-        g[k] = ld4(dy.p + (long long)ni * dy.sn + (long long)yo[a] * dy.sy + (long long)xo[b] * dy.sx + c);
-        if (kind != 0)
-          am[k] = *reinterpret_cast<const uchar4*>(idx + (((long long)ni * ho + yo[a]) * wo + xo[b]) * (c4 * 4) + c);
-      }
-    }
-    float* d = dx + (long long)ni * d_sn + (long long)y * d_sy + (long long)x * d_sx + c;
-    float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (accumulate) old = *reinterpret_cast<const float4*>(d);
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (chan_scale) sc = ld4(chan_scale + (long long)ni * (c4 * 4) + c);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < U; ++u) {
+      const unsigned i = i0 + u * step;
+      dptr[u] = nullptr;
+      if (i >= total) continue;
+      const unsigned cg = i % (unsigned)c4;
+      unsigned p = i / (unsigned)c4;
+      const unsigned x = p % (unsigned)w;
+      p /= (unsigned)w;
+      const unsigned y = p % (unsigned)h;
+      const unsigned ni = p / (unsigned)h;
+      const int c = cg * 4;
+      // windows: 2*yo-1 <= y <= 2*yo+1  ->  yo in {y/2, (y+1)/2}
+      const unsigned yo[2] = {y / 2, (y + 1) / 2}, xo[2] = {x / 2, (x + 1) / 2};
+      const bool vy[2] = {true, (y & 1u) && yo[1] < ho}, vx[2] = {true, (x & 1u) && xo[1] < wo};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int a = k >> 1, b = k & 1;
-      if (kind == 0) {
-        acc.x += g[k].x; acc.y += g[k].y; acc.z += g[k].z; acc.w += g[k].w;
-      } else {
-        const unsigned t = (y - (2 * yo[a] - 1)) * 3 + (x - (2 * xo[b] - 1));
-        if (am[k].x == t) acc.x += g[k].x;
-        if (am[k].y == t) acc.y += g[k].y;
-        if (am[k].z == t) acc.z += g[k].z;
-        if (am[k].w == t) acc.w += g[k].w;
+      for (int k = 0; k < 4; ++k) {
+        const int a = k >> 1, b = k & 1;
+        g[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (KIND != 0) {
+          am[u][k] = make_uchar4(255, 255, 255, 255);
+          tk[u][k] = (y - (2 * yo[a] - 1)) * 3 + (x - (2 * xo[b] - 1));
+        }
+        if (vy[a] && vx[b]) {
+          g[u][k] = ld4(dy.p + (long long)ni * dy.sn + (long long)yo[a] * dy.sy + (long long)xo[b] * dy.sx + c);
+          if constexpr (KIND != 0)
+            am[u][k] = *reinterpret_cast<const uchar4*>(idx + (((long long)ni * ho + yo[a]) * wo + xo[b]) * (c4 * 4) + c);
+        }
       }
+      dptr[u] = dx + (long long)ni * d_sn + (long long)y * d_sy + (long long)x * d_sx + c;
+      old[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (accumulate) old[u] = *reinterpret_cast<const float4*>(dptr[u]);
+      sc[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (chan_scale) sc[u] = ld4(chan_scale + (long long)ni * (c4 * 4) + c);
     }
-    if (kind == 0) {
-      acc.x /= 9.f; acc.y /= 9.f; acc.z /= 9.f; acc.w /= 9.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!dptr[u]) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (KIND == 0) {
+          acc.x += g[u][k].x; acc.y += g[u][k].y; acc.z += g[u][k].z; acc.w += g[u][k].w;
+        } else {
+          const unsigned t = tk[u][k];
+          if (am[u][k].x == t) acc.x += g[u][k].x;
+          if (am[u][k].y == t) acc.y += g[u][k].y;
+          if (am[u][k].z == t) acc.z += g[u][k].z;
+          if (am[u][k].w == t) acc.w += g[u][k].w;
+        }
+      }
+      if constexpr (KIND == 0) {
+        acc.x /= 9.f; acc.y /= 9.f; acc.z /= 9.f; acc.w /= 9.f;
+      }
+      acc.x = acc.x * sc[u].x + old[u].x; acc.y = acc.y * sc[u].y + old[u].y;
+      acc.z = acc.z * sc[u].z + old[u].z; acc.w = acc.w * sc[u].w + old[u].w;
+      *reinterpret_cast<float4*>(dptr[u]) = acc;
     }
-    acc.x = acc.x * sc.x + old.x; acc.y = acc.y * sc.y + old.y; acc.z = acc.z * sc.z + old.z; acc.w = acc.w * sc.w + old.w;
-    *reinterpret_cast<float4*>(d) = acc;
   }
 }
 
@@ -1186,8 +1207,12 @@ extern "C" int pmfb_pool3s2_bwd(int32_t kind, const pmfb_view* dy, int32_t n, in
   const long long total = (long long)n * h * w * (c / 4);
   if (total == 0) return PMFB_OK;
   REQ(total < (1ll << 32), "pool3s2_bwd: tensor too large for 32-bit indexing");
-  pool3s2_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(kind, ev(dy), n, h, w, c / 4, chan_scale, dx, d_sn, d_sy,
-                                                                             d_sx, idx, accumulate);
+  if (kind == 0)
+    pool3s2_bwd_kernel<0><<<grid_for(total, 512), 256, 0, (cudaStream_t)stream>>>(ev(dy), n, h, w, c / 4, chan_scale, dx, d_sn, d_sy, d_sx,
+                                                                                  idx, accumulate);
+  else
+    pool3s2_bwd_kernel<1><<<grid_for(total, 512), 256, 0, (cudaStream_t)stream>>>(ev(dy), n, h, w, c / 4, chan_scale, dx, d_sn, d_sy, d_sx,
+                                                                                  idx, accumulate);
   PMFB_LAUNCH_CHECK("pool3s2_bwd_kernel");
   return PMFB_OK;
 }
