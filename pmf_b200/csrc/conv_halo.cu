@@ -137,7 +137,14 @@ __device__ __forceinline__ void mma_issue_loop(const HaloK& P, HCtrl* ctrl, uint
               for (int k = 0; k < 4; ++k)
                 umma_issue<F16>(d_base + n_tile, a_lo + j_step + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc, accumulate | (uint32_t)k);
             }
-          } else {  // partial last slab (e.g. 32 channels in a 64-channel 16-bit slab)
+          } else if (nk == 2) {  // 32 channels in a 16-bit slab (64-byte operand rows)
+            umma_issue<F16>(d_base, a_lo, hi_a, b_lo, hi_b, idesc, accumulate);
+            umma_issue<F16>(d_base, a_lo + 2u, hi_a, b_lo + 2u, hi_b, idesc, 1u);
+            if (two) {
+              umma_issue<F16>(d_base + n_tile, a_lo + j_step, hi_a, b_lo, hi_b, idesc, accumulate);
+              umma_issue<F16>(d_base + n_tile, a_lo + j_step + 2u, hi_a, b_lo + 2u, hi_b, idesc, 1u);
+            }
+          } else {  // other partial last slabs
             for (int k = 0; k < nk; ++k) umma_issue<F16>(d_base, a_lo + 2u * k, hi_a, b_lo + 2u * k, hi_b, idesc, accumulate | (uint32_t)k);
             if (two)
               for (int k = 0; k < nk; ++k)
@@ -319,6 +326,13 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                 if (i < nq) r1v[i] = ld4(r2p + 4 * i);
             }
           }
+          // bias vector of this unit: fetched from shared memory while the TMEM load is in flight
+          float4 bv[8];
+          if constexpr ((EPI & kEpiB1) != 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i < nq) bv[i] = *reinterpret_cast<const float4*>(sv + kHMaxC + c0 + 4 * i);
+          }
           tmem_ld_wait();
           if (tma_store) {  // the previous unit's store must have finished reading the staging tile
             if (lane == 0) bulk_wait_group_read0();
@@ -336,8 +350,9 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                   for (int e = 0; e < 4; ++e) {
                     float a = v[8 * i2 + 2 * e], b = v[8 * i2 + 2 * e + 1];
                     if constexpr ((EPI & kEpiB1) != 0) {
-                      a += sv[kHMaxC + c0 + 8 * i2 + 2 * e];
-                      b += sv[kHMaxC + c0 + 8 * i2 + 2 * e + 1];
+                      const float4 bb = bv[2 * i2 + (e >> 1)];
+                      a += (e & 1) ? bb.z : bb.x;
+                      b += (e & 1) ? bb.w : bb.y;
                     }
                     if constexpr ((EPI & kEpiLeaky) != 0) {
                       a = fmaxf(a, 0.01f * a);
@@ -362,10 +377,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
                   const float4 a = *reinterpret_cast<const float4*>(sv + c0 + 4 * i);
                   o.x *= a.x; o.y *= a.y; o.z *= a.z; o.w *= a.w;
                 }
-                if constexpr ((EPI & kEpiB1) != 0) {
-                  const float4 b = *reinterpret_cast<const float4*>(sv + kHMaxC + c0 + 4 * i);
-                  o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                }
+                if constexpr ((EPI & kEpiB1) != 0) { o.x += bv[i].x; o.y += bv[i].y; o.z += bv[i].z; o.w += bv[i].w; }
                 if constexpr ((EPI & kEpiR1) != 0) { o.x += r1v[i].x; o.y += r1v[i].y; o.z += r1v[i].z; o.w += r1v[i].w; }
                 if constexpr ((EPI & kEpiLeaky) != 0) {
                   o.x = fmaxf(o.x, 0.01f * o.x); o.y = fmaxf(o.y, 0.01f * o.y);

@@ -380,13 +380,13 @@ pool3s2_kernel(int kind, EpiView xin, int n, int h, int w, int c4, const float* 
 // gather form: every input pixel sums the (at most 4) output windows that cover it.  32-bit index arithmetic and all
 // four candidate loads (plus the accumulate read) issued before the first use: the kernel is a pure HBM stream.
 template <int KIND>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, KIND == 0 ? 3 : 2)
 pool3s2_bwd_kernel(EpiView dy, int n, int h, int w, int c4, const float* __restrict__ chan_scale, float* dx,
                    long long d_sn, long long d_sy, long long d_sx, const uint8_t* __restrict__ idx, int accumulate) {
   // Two (pixel, 4-channel group) items per thread and trip, every load of both issued before the first use: the kernel is a
   // gather (<= 4 pooled gradients per pixel, mostly L2 hits) plus one full-resolution read-modify-write stream, and with one
   // item per trip it ran latency-bound at 1.9 TB/s.
-  constexpr int U = KIND == 0 ? 2 : 1;
+  constexpr int U = 2;
   const unsigned ho = h / 2, wo = w / 2;
   const unsigned total = (unsigned)n * h * w * c4;  // host guarantees < 2^32
   const unsigned step = gridDim.x * blockDim.x;
