@@ -106,7 +106,7 @@ def test_pmf_dropout_on_matches_oracle_with_shared_masks(dev, monkeypatch):  # n
 def test_reference_gpu_tf32_deviation_recorded_beside_ours(dev):  # noqa: F811
     """the reference's OWN GPU path (eager PyTorch, cuDNN with TF32 allowed — torch's default) is not
     bit-stable against the fp32 CPU oracle either.  Measured on the same inputs as ours: default-init train-mode forward
-    (dropout inactive), and recorded next to our default (kind::tf32) and precise (3xtf32) modes."""
+    (dropout inactive), and recorded next to our default (f16), kind::tf32 and precise (3xtf32) modes."""
     import pmf_b200
     m, sd = _model(dev)
     m.train()
@@ -127,7 +127,7 @@ def test_reference_gpu_tf32_deviation_recorded_beside_ours(dev):  # noqa: F811
             rep[name] = dict(lidar=_maxrel(gl.cpu(), rl), camera=_maxrel(gc.cpu(), rc))
     finally:
         torch.backends.cudnn.allow_tf32 = old
-    for name, mode in (("ours_tf32", "tf32"), ("ours_3xtf32", "3xtf32")):
+    for name, mode in (("ours_f16", "f16"), ("ours_tf32", "tf32"), ("ours_3xtf32", "3xtf32")):
         m.load_state_dict(sd)
         with pmf_b200.precision(mode), torch.no_grad():
             lid, cam = m(x[:, 0:5], x[:, 5:8])
@@ -136,3 +136,6 @@ def test_reference_gpu_tf32_deviation_recorded_beside_ours(dev):  # noqa: F811
     assert rep["ours_3xtf32"]["lidar"] < 1e-3 and rep["ours_3xtf32"]["camera"] < 1e-3, rep
     # the fast mode stays in the reference GPU path's own error class
     assert rep["ours_tf32"]["lidar"] <= 4 * rep["reference_gpu_cudnn_tf32"]["lidar"] + 2e-3, rep
+    # ... and so does the default "f16" mode (fp16 operands for >= 64-channel layers, fp16 pre-BatchNorm activations)
+    assert rep["ours_f16"]["lidar"] <= 4 * rep["reference_gpu_cudnn_tf32"]["lidar"] + 2e-3, rep
+    assert rep["ours_f16"]["camera"] <= 4 * rep["reference_gpu_cudnn_tf32"]["camera"] + 2e-3, rep
