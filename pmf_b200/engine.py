@@ -760,69 +760,89 @@ class Engine:
         n, h, w, _ = x.shape
         _, oh, ow, co = (d_pre if d_pre is not None else d16).shape
         assert co == cp.c_out_p
-        # ---- wgrad -> packed [taps][c_in_p][c_out_p] (split-K atomics; buffer zeroed here) -> OIHW
-        batched = self._wg_arena is not None and cp.name in self._wg_off
-        if batched:
-            off, size = self._wg_off[cp.name]
-            packed = self._wg_arena[off:off + size]
-        else:
-            packed = torch.empty(cp.taps * cp.c_in_p * cp.c_out_p, device=self.device, dtype=torch.float32)
-            L.call("pmfb_memset_zero", packed.data_ptr(), packed.numel() * 4, self.st)
-        d = WgradDesc()
-        d.c_in, d.c_out, d.n_taps = cp.c_in_p, cp.c_out_p, cp.taps
-        for i, (dc, dw, dp, dh, _wi) in enumerate(cp.fwd_taps()):
-            d.tap_dc[i], d.tap_dw[i], d.tap_dp[i], d.tap_dh[i] = dc, dw, dp, dh
-        d.n_batch, d.out_h, d.out_w = n, oh, ow
-        d.ptile_w, d.ptile_h = _pick_tile(oh, ow, 32)
-        d.n_tile = min(256, _rup(cp.c_out_p, 32))
-        total_pt = (_rup(ow, d.ptile_w) // d.ptile_w) * (_rup(oh, d.ptile_h) // d.ptile_h) * n
-        base = ((cp.taps * (_rup(cp.c_in_p, 32) // 32) + 3) // 4) * ((cp.c_out_p + d.n_tile - 1) // d.n_tile)
-        d.ksplit = max(1, min(max(1, total_pt // 4), (2 * self.n_sm + base - 1) // base))
-        d.dw = packed.data_ptr()
-        main_st = self.st
+        # Order of enqueue: the event "d_pre is ready" is recorded first, then the dgrad goes to the main stream and only then
+        # the wgrad to the side stream.  Both become runnable at the same moment and their CTAs cannot share an SM (180 KB +
+        # 190 KB of shared memory): the dgrad is on the critical path, the wgrad can fill in next to the BatchNorm-backward
+        # kernels of the following layer, so the dgrad should win the SMs.
+        ev_ready = None
         if self.use_side:
             if self.side is None:
                 self.side = _side_stream(self.device)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.device))   # d_pre (and, the first time, the zeroed arena) are ready
-            self.side.wait_event(ev)
-            self.st = self.side.cuda_stream
-            self._side_keep.append((x.t, d_pre, packed))
-        if self.precise:
-            # dw = x_hi*dy_hi + x_hi*dy_lo + x_lo*dy_hi: three launches accumulating into the same packed gradient
-            x_hi, x_lo = self.split(x.t, 2), self.split(x.t, 3)
-            dy_hi, dy_lo = self.split(d_pre, 2), self.split(d_pre, 3)
-            pairs = ((x_hi, dy_hi), (x_hi, dy_lo), (x_lo, dy_hi))
-        else:
-            pairs = ((x.t, d_pre),)
-            # "f16" mode: bf16 shadows of both operands (kind::f16, K = 16 pixels per UMMA) where the library takes them
-            if (self.h16 and H16_WGRAD and d16 is not None and cp.stride == 1 and cp.c_in_p % 8 == 0
-                    and cp.c_in_p >= H16_WGRAD_MIN and cp.c_out_p >= H16_WGRAD_MIN):
-                d.x = self._tma_src(x.t, cp.c_in_p, False)
-                d.dy = self._tma_src(d16, cp.c_out_p)
-                if L.query("pmfb_wgrad16_ok", C.byref(d)) == 1:
-                    xb = self._ensure_shadow(x, bf16=True)  # written by x's producer, else converted here once
-                    if xb is None:
-                        xb = torch.empty(x.t.shape, device=self.device, dtype=torch.bfloat16)
-                        L.call("pmfb_convert16", C.byref(_view(x.t)), n, h, w, cp.c_in_p, xb.data_ptr(), xb.stride(0),
-                               xb.stride(1), xb.stride(2), L.DT_BF16, self.st)
-                    pairs = ((xb, d16),)
-                    d.dtype = L.DT_BF16
-            assert pairs[0][1] is not None, "the fp32 output gradient was skipped for a layer whose wgrad needs it: " + cp.name
-        for xa, dya in pairs:
-            d.x = self._tma_src(xa, cp.c_in_p, cp.stride == 2)
-            d.dy = self._tma_src(dya, cp.c_out_p)
-            L.call("pmfb_conv_wgrad", C.byref(d), self.st)
+            ev_ready = torch.cuda.Event()
+            ev_ready.record(torch.cuda.current_stream(self.device))   # d_pre (and, the first time, the zeroed arena) are ready
+        main_st = self.st
+
+        def launch_wgrad():
+            if not self.use_side:
+                return _wgrad_body()
+            # Everything the wgrad allocates (split operands of the precise mode, lazily converted shadows, the packed
+            # gradient) must come from the SIDE stream's allocator pool: a block the main stream has just released (the
+            # dgrad's temporaries above) may still be read by a kernel in flight there.
+            with torch.cuda.stream(self.side):
+                return _wgrad_body()
+
+        def _wgrad_body():
+            # ---- wgrad -> packed [taps][c_in_p][c_out_p] (split-K atomics; buffer zeroed here) -> OIHW
             if self.use_side:
-                self._side_keep.append((xa, dya))
-        gw = self._pgrad(cp.name + ".weight", cp.weight)
-        if not batched:
-            L.call("pmfb_unpack_wgrad", packed.data_ptr(), cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0, cp.c_out_p,
-                   cp.c_in_p, gw.data_ptr(), 0, self.st)
-        self.st = main_st
-        self.param_grads[cp.name + ".weight"] = gw
+                self.side.wait_event(ev_ready)
+                self.st = self.side.cuda_stream
+            batched = self._wg_arena is not None and cp.name in self._wg_off
+            if batched:
+                off, size = self._wg_off[cp.name]
+                packed = self._wg_arena[off:off + size]
+            else:
+                packed = torch.empty(cp.taps * cp.c_in_p * cp.c_out_p, device=self.device, dtype=torch.float32)
+                L.call("pmfb_memset_zero", packed.data_ptr(), packed.numel() * 4, self.st)
+            d = WgradDesc()
+            d.c_in, d.c_out, d.n_taps = cp.c_in_p, cp.c_out_p, cp.taps
+            for i, (dc, dw, dp, dh, _wi) in enumerate(cp.fwd_taps()):
+                d.tap_dc[i], d.tap_dw[i], d.tap_dp[i], d.tap_dh[i] = dc, dw, dp, dh
+            d.n_batch, d.out_h, d.out_w = n, oh, ow
+            d.ptile_w, d.ptile_h = _pick_tile(oh, ow, 32)
+            d.n_tile = min(256, _rup(cp.c_out_p, 32))
+            total_pt = (_rup(ow, d.ptile_w) // d.ptile_w) * (_rup(oh, d.ptile_h) // d.ptile_h) * n
+            base = ((cp.taps * (_rup(cp.c_in_p, 32) // 32) + 3) // 4) * ((cp.c_out_p + d.n_tile - 1) // d.n_tile)
+            d.ksplit = max(1, min(max(1, total_pt // 4), (2 * self.n_sm + base - 1) // base))
+            d.dw = packed.data_ptr()
+            if self.use_side:
+                self._side_keep.append((x.t, d_pre, packed))
+            if self.precise:
+                # dw = x_hi*dy_hi + x_hi*dy_lo + x_lo*dy_hi: three launches accumulating into the same packed gradient
+                x_hi, x_lo = self.split(x.t, 2), self.split(x.t, 3)
+                dy_hi, dy_lo = self.split(d_pre, 2), self.split(d_pre, 3)
+                pairs = ((x_hi, dy_hi), (x_hi, dy_lo), (x_lo, dy_hi))
+            else:
+                pairs = ((x.t, d_pre),)
+                # "f16" mode: bf16 shadows of both operands (kind::f16, K = 16 pixels per UMMA) where the library takes them
+                if (self.h16 and H16_WGRAD and d16 is not None and cp.stride == 1 and cp.c_in_p % 8 == 0
+                        and cp.c_in_p >= H16_WGRAD_MIN and cp.c_out_p >= H16_WGRAD_MIN):
+                    d.x = self._tma_src(x.t, cp.c_in_p, False)
+                    d.dy = self._tma_src(d16, cp.c_out_p)
+                    if L.query("pmfb_wgrad16_ok", C.byref(d)) == 1:
+                        xb = self._ensure_shadow(x, bf16=True)  # written by x's producer, else converted here once
+                        if xb is None:
+                            xb = torch.empty(x.t.shape, device=self.device, dtype=torch.bfloat16)
+                            L.call("pmfb_convert16", C.byref(_view(x.t)), n, h, w, cp.c_in_p, xb.data_ptr(), xb.stride(0),
+                                   xb.stride(1), xb.stride(2), L.DT_BF16, self.st)
+                        pairs = ((xb, d16),)
+                        d.dtype = L.DT_BF16
+                assert pairs[0][1] is not None, "the fp32 output gradient was skipped for a layer whose wgrad needs it: " + cp.name
+            for xa, dya in pairs:
+                d.x = self._tma_src(xa, cp.c_in_p, cp.stride == 2)
+                d.dy = self._tma_src(dya, cp.c_out_p)
+                L.call("pmfb_conv_wgrad", C.byref(d), self.st)
+                if self.use_side:
+                    self._side_keep.append((xa, dya))
+            gw = self._pgrad(cp.name + ".weight", cp.weight)
+            if not batched:
+                L.call("pmfb_unpack_wgrad", packed.data_ptr(), cp.c_out, cp.c_in, cp.kh, cp.kw, 1 if cp.stem else 0, cp.c_out_p,
+                       cp.c_in_p, gw.data_ptr(), 0, self.st)
+            self.st = main_st
+            self.param_grads[cp.name + ".weight"] = gw
+
         # ---- dgrad
         if not x.needs_grad:
+            launch_wgrad()
             return
         assert not cp.stem and cp.c_in_p == cp.c_in
         gx, acc = x.grad_target()
@@ -832,6 +852,7 @@ class Engine:
             taps = [(0, -dw, 0, -dh, wi) for (_dc, dw, _dp, dh, wi) in cp.fwd_taps()]
             self._conv_launch(d_pre, cp.c_out_p, False, w_dgrad, cp.c_in_p, taps, n, h, w, gx,
                               self._epi(r1=gx if acc else None, rnd=rnd), x16=d16, w16=e.get("dgrad16"), dt16=L.DT_BF16)
+            launch_wgrad()
             return
         # stride 2: one stride-1 convolution over dy per input parity class
         for py in (0, 1):
@@ -849,6 +870,7 @@ class Engine:
                     continue
                 self._conv_launch(d_pre, cp.c_out_p, False, w_dgrad, cp.c_in_p, taps, n, h // 2, w // 2, sub,
                                   self._epi(r1=sub if acc else None, rnd=rnd), x16=d16, w16=e.get("dgrad16"), dt16=L.DT_BF16)
+        launch_wgrad()
 
     def _bias_grad(self, cp, colsum64):
         gb = self._pgrad(cp.name + ".bias", cp.bias)
