@@ -11,6 +11,7 @@ Reference semantics (paths relative to the reference tree):
   conv_act_bn   nn.Conv2d -> LeakyReLU -> BatchNorm2d       salsanext.py:27-33,73-90,145-160; pmf_net.py:13-18,187-209
   conv_bn       nn.Conv2d -> BatchNorm2d -> ReLU/Sigmoid    torchvision BasicBlock/Bottleneck; pmf_net.py:20-29,35
 """
+import contextlib
 import ctypes as C
 import math
 import os
@@ -32,6 +33,8 @@ H16_WGRAD = os.environ.get("PMFB_H16_WGRAD", "1") != "0"
 PRE_BN_HALF = os.environ.get("PMFB_PRE_BN_HALF", "1") != "0"
 # ... and the BatchNorm finalisation of such a layer runs inside its BN-apply launch (pmfb_pointwise16_bn)
 BN_FUSE_FINALIZE = os.environ.get("PMFB_BN_FUSE_FINALIZE", "1") != "0"
+# forward: the camera stream (encoder + decoder) is enqueued on the auxiliary stream, concurrently with the LiDAR stream
+FWD_BRANCH = os.environ.get("PMFB_FWD_BRANCH", "1") != "0"
 
 
 def _rup(x, m):
@@ -64,7 +67,7 @@ def _p(t):
 
 class Act:
     """An NHWC activation: ``t`` is a (N,H,W,C) torch view; slices share the root's gradient buffer."""
-    __slots__ = ("t", "root", "c0", "needs_grad", "_round_grad", "grad", "gcov", "h", "hcov", "hb", "hbcov")
+    __slots__ = ("t", "root", "c0", "needs_grad", "_round_grad", "grad", "gcov", "h", "hcov", "hb", "hbcov", "ready")
 
     def __init__(self, t, root=None, c0=0, needs_grad=True):
         self.t = t
@@ -78,6 +81,7 @@ class Act:
         self.hcov = []           # root only: channel intervals of the shadow that hold current values
         self.hb = None           # root only ("f16" mode, recording): bf16 shadow of t, the x operand of the bf16 wgrad
         self.hbcov = []
+        self.ready = None        # root only: event recorded when a forward branch (Engine.branch) finished producing t
 
     # ---- 16-bit shadow ("f16" precision mode)
     def shadow(self, bf16=False):
@@ -472,6 +476,55 @@ class Engine:
         self.side = None
         self._side_keep = []
         self.use_side = os.environ.get("PMFB_WGRAD_STREAM", "1") != "0" and str(device).startswith("cuda")
+        self.use_branch = FWD_BRANCH and str(device).startswith("cuda")
+        self._in_branch = False
+        self._branch_done = None
+
+    # ------------------------------------------------------------------------------------------ forward branches
+    @contextlib.contextmanager
+    def branch(self):
+        """Forward only: the ops issued inside run on the auxiliary stream, concurrently with what the caller issues on the
+        main stream afterwards (PMF: the camera stream next to the LiDAR stream — two chains that each alternate a tensor-core
+        convolution with HBM-bound elementwise passes, so one chain's elementwise kernels run next to the other's
+        convolutions).  Tensors produced inside are handed over with mark_ready / wait_ready; join_branch() before anything
+        on the main stream may depend on all of it.  Allocations inside come from the auxiliary stream's allocator pool."""
+        if not self.use_branch:
+            yield
+            return
+        if self.side is None:
+            self.side = _side_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))  # inputs, packed weights, zeroed scratch are ready
+        self.side.wait_event(ev)
+        main_st = self.st
+        with torch.cuda.stream(self.side):
+            self.st = self.side.cuda_stream
+            self._in_branch = True
+            try:
+                yield
+            finally:
+                self._in_branch = False
+                self.st = main_st
+                self._branch_done = torch.cuda.Event()
+                self._branch_done.record(self.side)
+
+    def mark_ready(self, act):
+        """Inside branch(): ``act`` is complete at this point of the auxiliary stream."""
+        if self._in_branch:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            act.root.ready = ev
+
+    def wait_ready(self, act):
+        """The current stream waits for a tensor a branch produced (no-op for everything else)."""
+        ev = act.root.ready
+        if ev is not None and not self._in_branch:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def join_branch(self):
+        if self._branch_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._branch_done)
+            self._branch_done = None
 
     # ------------------------------------------------------------------------------------------ helpers
     def _pgrad(self, name, like):

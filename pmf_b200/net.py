@@ -142,6 +142,7 @@ def resnet_encoder(E, img7, p, backbone):
                 c_out = E.P.bn(bp + (".bn2" if block is basic_block else ".bn3")).c
                 mask = E.mask_for("%s.dropout.layer%d" % (p, li), x.shape[0], c_out)
             x = block(E, x, bp, has_ds, mask=mask)
+        E.mark_ready(x)  # consumers on another stream (Engine.branch) wait for this point only, not for the whole encoder
         feats.append(x)
     return feats
 
@@ -160,6 +161,7 @@ def salsanext_fusion(E, pcd, feats, p, nclasses):
         hh, ww = x.shape[1] // 2, x.shape[2] // 2
         cat = E.new(n, hh, ww, c + img.c)
         _, skip = res_block(E, x, "%s.resBlock%d" % (p, i + 1), pooling=True, drop_out=(i > 0), pool_out=cat.slice(0, c))
+        E.wait_ready(img)
         E.copy(img, cat.slice(c, c + img.c))
         x = fusion_block(E, cat, c, "%s.fusionblock_%d" % (p, i + 1))
         skips.append(skip)
@@ -306,9 +308,11 @@ def pmf_forward(E, pcd_feature, img_feature, backbone, nclasses):
 
 def pmf_forward_packed(E, pcd, img7, backbone, nclasses):
     """The graph proper, from the packed NHWC inputs (pcd: channel-padded; img7: horizontally unrolled RGB)."""
-    feats = resnet_encoder(E, img7, "camera_stream_encoder", backbone)
+    with E.branch():  # the camera stream runs next to the LiDAR stream; the four feature maps are handed over by events
+        feats = resnet_encoder(E, img7, "camera_stream_encoder", backbone)
+        camera_logits = rgb_decoder(E, feats, "camera_stream_decoder")
     lidar_logits = salsanext_fusion(E, pcd, feats, "lidar_stream", nclasses)
-    camera_logits = rgb_decoder(E, feats, "camera_stream_decoder")
+    E.join_branch()
     lidar = E.softmax_nchw(lidar_logits, nclasses)
     camera = E.softmax_nchw(camera_logits, nclasses)
     E.finish_forward()
