@@ -35,6 +35,11 @@ PRE_BN_HALF = os.environ.get("PMFB_PRE_BN_HALF", "1") != "0"
 BN_FUSE_FINALIZE = os.environ.get("PMFB_BN_FUSE_FINALIZE", "1") != "0"
 # forward: the camera stream (encoder + decoder) is enqueued on the auxiliary stream, concurrently with the LiDAR stream
 FWD_BRANCH = os.environ.get("PMFB_FWD_BRANCH", "1") != "0"
+# backward: the camera stream's closures on a second auxiliary stream next to the LiDAR stream's (Engine._backward_order).
+# OFF by default: correct (tests/test_gpu_parity.py::test_backward_branch_order_matches_plain_order) but measured 0.8 ms
+# SLOWER at B=8, 480x640 — the backward is already saturated by the weight-gradient overlap, a third chain only adds
+# contention (kernel durations sum to 77 ms instead of 70 ms over the same 51 ms step).
+BWD_BRANCH = os.environ.get("PMFB_BWD_BRANCH", "0") != "0"
 
 
 def _rup(x, m):
@@ -396,9 +401,10 @@ class WeightCache:
 _side_streams = {}
 
 
-def _side_stream(device):
-    """One auxiliary CUDA stream per device for the weight-gradient kernels (see Engine._conv_bwd)."""
-    key = str(device)
+def _side_stream(device, which=0):
+    """Auxiliary CUDA streams per device: 0 for the weight-gradient kernels (Engine._conv_bwd) and the forward camera branch,
+    1 for the backward camera branch."""
+    key = "%s#%d" % (device, which)
     st = _side_streams.get(key)
     if st is None:
         st = _side_streams[key] = torch.cuda.Stream(device=device)
@@ -479,6 +485,10 @@ class Engine:
         self.use_branch = FWD_BRANCH and str(device).startswith("cuda")
         self._in_branch = False
         self._branch_done = None
+        self._branch_span = None   # [first, one-past-last] tape index recorded inside branch()
+        self._marks = []           # (root Act, tape length when a branch marked it ready)
+        self._waits = []           # (root Act, tape length when the main stream waited for it)
+        self.side2 = None
 
     # ------------------------------------------------------------------------------------------ forward branches
     @contextlib.contextmanager
@@ -497,6 +507,7 @@ class Engine:
         ev.record(torch.cuda.current_stream(self.device))  # inputs, packed weights, zeroed scratch are ready
         self.side.wait_event(ev)
         main_st = self.st
+        self._branch_span = [len(self.tape), None]
         with torch.cuda.stream(self.side):
             self.st = self.side.cuda_stream
             self._in_branch = True
@@ -505,6 +516,7 @@ class Engine:
             finally:
                 self._in_branch = False
                 self.st = main_st
+                self._branch_span[1] = len(self.tape)
                 self._branch_done = torch.cuda.Event()
                 self._branch_done.record(self.side)
 
@@ -514,12 +526,14 @@ class Engine:
             ev = torch.cuda.Event()
             ev.record(self.side)
             act.root.ready = ev
+            self._marks.append((act.root, len(self.tape)))
 
     def wait_ready(self, act):
         """The current stream waits for a tensor a branch produced (no-op for everything else)."""
         ev = act.root.ready
         if ev is not None and not self._in_branch:
             torch.cuda.current_stream(self.device).wait_event(ev)
+            self._waits.append((act.root, len(self.tape)))  # the closure recorded next consumes it on the main stream
 
     def join_branch(self):
         if self._branch_done is not None:
@@ -743,15 +757,107 @@ class Engine:
     # ---- backward segments (graph mode): the reversed tape is cut into K contiguous pieces of roughly equal convolution
     # work; each piece becomes its own CUDA graph and autograd node, so that DDP's bucketed all-reduce of a piece's
     # parameter gradients (tasks/pmf/trainer.py:38-39) overlaps the backward of the next pieces.
+    def _backward_order(self):
+        """Execution order of the backward: entries ("fn", tape index, "main" | "cam"), ("rec", tag, key), ("wait", tag, key).
+
+        Without a forward branch: the reversed tape on the main stream.  With one (PMF: camera stream = tape [b0, b1), LiDAR
+        stream = the rest) the camera stream's closures run on a second auxiliary stream next to the LiDAR stream's.  Both
+        chains write the gradients of the J shared feature maps feats[0..J-1], so every writer of one buffer is ordered by
+        an event:
+          * the decoder's backward (it only needs the camera logits' gradient) goes first and is the FIRST writer of every
+            feats[i].grad; the LiDAR chain waits for it before its first feature-map copy backward W[J-1];
+          * encoder layer j (reads feats[j-1].grad, accumulates into feats[j-2].grad) is released after W[j-2], i.e. after
+            the LiDAR chain's own accumulation into the buffer layer j writes, one stage later than its input would allow;
+          * layer 1 (and the stem) follow layer 2 in stream order.
+        Segments (plan_segments) end with a join of both auxiliary streams, so a wait whose record fell into an earlier
+        segment is simply dropped."""
+        n = len(self.tape)
+        plain = [("fn", i, "main") for i in range(n - 1, -1, -1)]
+        span = self._branch_span
+        if not (BWD_BRANCH and self.use_branch and span and span[1] is not None and len(self._marks) >= 2
+                and len(self._marks) == len(self._waits)):
+            return plain
+        b0, b1 = span
+        marks = [m for (_r, m) in self._marks]
+        W = []
+        for (root, _m), (wroot, wi) in zip(self._marks, self._waits):
+            if wroot is not root or not (b1 <= wi < n) or getattr(self.tape[wi], "copy_src_root", None) is not root:
+                return plain
+            W.append(wi)
+        if b0 != 0 or sorted(W) != W or sorted(marks) != marks or marks[0] <= b0 or marks[-1] > b1:
+            return plain
+        J = len(marks)
+        groups, lo = [], b0
+        for m in marks:  # groups[j-1] = closures of encoder layer j (the stem rides with layer 1), in backward order
+            groups.append(list(range(m - 1, lo - 1, -1)))
+            lo = m
+        order = [("fn", i, "cam") for i in range(b1 - 1, marks[-1] - 1, -1)] + [("rec", "cam", "D")]
+        release = {W[j - 2]: j for j in range(J, 1, -1)}
+        first_w = max(W)
+        for i in range(n - 1, b1 - 1, -1):
+            if i == first_w:
+                order.append(("wait", "main", "D"))
+            order.append(("fn", i, "main"))
+            j = release.get(i)
+            if j is not None:
+                key = "W%d" % i
+                order += [("rec", "main", key), ("wait", "cam", key)] + [("fn", c, "cam") for c in groups[j - 1]]
+        order += [("fn", c, "cam") for c in groups[0]]
+        return order
+
+    def _run_entries(self, entries):
+        """Executes entries of _backward_order (the current stream is the main stream)."""
+        main = torch.cuda.current_stream(self.device)
+        main_st = self.st
+        has_cam = self.use_branch and any(e[0] == "fn" and e[2] == "cam" for e in entries)
+        bev = {}
+        if has_cam:
+            if self.side2 is None:
+                self.side2 = _side_stream(self.device, 1)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side2.wait_event(ev)
+        for e in entries:
+            if e[0] == "fn":
+                fn = self.tape[e[1]]
+                if has_cam and e[2] == "cam":
+                    with torch.cuda.stream(self.side2):  # allocations from this stream's pool (see Engine.branch)
+                        self.st = self.side2.cuda_stream
+                        try:
+                            fn()
+                        finally:
+                            self.st = main_st
+                else:
+                    fn()
+            elif has_cam:
+                st = self.side2 if e[1] == "cam" else main
+                if e[0] == "rec":
+                    bev[e[2]] = torch.cuda.Event()
+                    bev[e[2]].record(st)
+                elif e[2] in bev:
+                    st.wait_event(bev[e[2]])
+        if has_cam:
+            ev = torch.cuda.Event()
+            ev.record(self.side2)
+            main.wait_event(ev)
+
     def plan_segments(self, k):
-        """Returns [(closures in execution order, parameter names produced)] * <= k for the recorded tape."""
-        rev = list(reversed(self.tape))
-        cost = [2.0 * getattr(f, "px", 0) * f.cp.taps * f.cp.c_in_p * f.cp.c_out_p if getattr(f, "cp", None) is not None else 0.0
-                for f in rev]
+        """Returns [(entries in execution order, parameter names produced)] * <= k for the recorded tape."""
+        order = self._backward_order()
+
+        def fn_of(e):
+            return self.tape[e[1]] if e[0] == "fn" else None
+
+        def cost_of(e):
+            f = fn_of(e)
+            if f is None or getattr(f, "cp", None) is None:
+                return 0.0
+            return 2.0 * getattr(f, "px", 0) * f.cp.taps * f.cp.c_in_p * f.cp.c_out_p
+        cost = [cost_of(e) for e in order]
         total = sum(cost) or 1.0
         segs, cur, acc, done = [], [], 0.0, 0.0
-        for f, c in zip(rev, cost):
-            cur.append(f)
+        for e, c in zip(order, cost):
+            cur.append(e)
             acc += c
             if len(segs) < k - 1 and done + acc >= total * (len(segs) + 1) / k:
                 segs.append(cur)
@@ -760,9 +866,10 @@ class Engine:
         if cur:
             segs.append(cur)
         out = []
-        for fs in segs:
+        for es in segs:
             names = []
-            for f in fs:
+            for e in es:
+                f = fn_of(e)
                 cp, bn = getattr(f, "cp", None), getattr(f, "bn", None)
                 if cp is not None:
                     names.append(cp.name + ".weight")
@@ -770,7 +877,7 @@ class Engine:
                         names.append(cp.name + ".bias")
                 if bn is not None:
                     names += [bn.name + ".weight", bn.name + ".bias"]
-            out.append((fs, names))
+            out.append((es, names))
         self.segments = out
         return out
 
@@ -786,10 +893,10 @@ class Engine:
         self._wg_arena = torch.empty(total, device=self.device, dtype=torch.float32)
         off = 0
         self._unpack_tables = []
-        for fs, _names in self.segments:
+        for es, _names in self.segments:
             jobs, start = [], 0
-            for f in fs:
-                cp = getattr(f, "cp", None)
+            for e in es:
+                cp = getattr(self.tape[e[1]], "cp", None) if e[0] == "fn" else None
                 if cp is None:
                     continue
                 size = cp.taps * cp.c_in_p * cp.c_out_p
@@ -1229,6 +1336,7 @@ class Engine:
                 gs, acc = src.grad_target()
                 self.pointwise(g, gs, mul=mv, r2=gs if acc else None, rnd=1 if src.round_grad else 0)
 
+            bwd.copy_src_root = src.root
             self.tape.append(bwd)
         return dst
 
@@ -1357,8 +1465,7 @@ class Engine:
 
     def run_backward(self):
         self.begin_backward()
-        for fn in reversed(self.tape):
-            fn()
+        self._run_entries(self._backward_order())
         self.join_side()
         for tab in (self._unpack_tables or []):
             if tab is not None:
@@ -1368,8 +1475,8 @@ class Engine:
 
     def begin_backward(self):
         self.st = torch.cuda.current_stream(self.device).cuda_stream
-        self.d64 = _Scratch(torch.float64, 1 << 17, self.device, self.st, zero=True)
-        self.f32.stream = self.st
+        self.d64 = _Scratch(torch.float64, 1 << 18, self.device, self.st, zero=True)  # one chunk for the whole backward: a
+        self.f32.stream = self.st                                                     # new one would be zeroed on THIS stream only
         if self._wg_arena is not None:
             L.call("pmfb_memset_zero", self._wg_arena.data_ptr(), self._wg_arena.numel() * 4, self.st)
 
@@ -1382,8 +1489,7 @@ class Engine:
         else:
             self.d64.stream = self.st
             self.f32.stream = self.st
-        for fn in self.segments[k][0]:
-            fn()
+        self._run_entries(self.segments[k][0])
         self.join_side()
         tab = self._unpack_tables[k] if self._unpack_tables else None
         if tab is not None:

@@ -12,6 +12,7 @@ called: the whole network runs as one autograd.Function over pmf_b200.engine.  T
 module with CPU tensors raises.
 """
 import contextlib
+import gc
 import os
 
 import torch
@@ -286,6 +287,25 @@ class _PMFFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
+@contextlib.contextmanager
+def _capture(graph, pool):
+    """torch.cuda.graph(...) with Python's cyclic garbage collector out of the way.  torch no longer collects before a
+    capture (torch.compiler.config.force_cudagraph_gc), and a capture here creates thousands of Python objects: if the
+    collector runs in the middle of it and frees a dead cycle that owns CUDA memory — a module whose graphs were just
+    evicted or replaced, an earlier model of the same process — the cudaFree in the capturing thread invalidates the
+    capture (cudaErrorStreamCaptureInvalidated at the next launch).  Collect first, keep the collector off until the graph
+    is closed."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph, pool=pool, capture_error_mode="thread_local"):  # NCCL watchdog threads may poll events
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
 GRAPH_CACHE = max(1, int(os.environ.get("PMFB_GRAPH_CACHE", "8")))
 
 
@@ -335,7 +355,7 @@ class _GraphedPMF:
             self.cache.build_table(G.ModuleParams(mod), record, self.dev)  # every weight packed by one launch per pass
         torch.cuda.synchronize(self.dev)
         l0 = _L.launches
-        with torch.cuda.graph(self.g_fwd, pool=self.pool, capture_error_mode="thread_local"):  # NCCL watchdog threads may poll events
+        with _capture(self.g_fwd, self.pool):
             E = Engine(G.ModuleParams(mod), self.dev, mod.training, record, self.cache, dropout=mod._dropout_masks())
             self.lidar, self.camera, self.ll, self.cl = G.pmf_forward_packed(E, self.pcd, self.img7, mod.image_backbone,
                                                                              mod.nclasses)
@@ -396,7 +416,7 @@ class _GraphedPMF:
         if not seg["captured"]:
             torch.cuda.synchronize(self.dev)
             l0 = _L.launches
-            with torch.cuda.graph(seg["graph"], pool=self.pool, capture_error_mode="thread_local"):
+            with _capture(seg["graph"], self.pool):
                 E.run_backward_segment(k)
             seg["calls"] = _L.launches - l0
             _L.launches = l0
@@ -667,7 +687,7 @@ class _GraphedEPMF:
         self.cache.build_table(G.ModuleParams(mod), False, self.dev)
         torch.cuda.synchronize(self.dev)
         l0 = _L.launches
-        with torch.cuda.graph(self.g, pool=self.pool, capture_error_mode="thread_local"):
+        with _capture(self.g, self.pool):
             E = Engine(G.ModuleParams(mod), self.dev, False, False, self.cache, dropout=False)
             self.lidar, self.camera, _, _ = G.epmf_forward_packed(E, self.pcd, self.img7, mod.image_backbone, mod.nclasses)
         self.n_calls = _L.launches - l0

@@ -269,3 +269,63 @@ def test_precise_mode_3xtf32_recovers_fp32_on_the_truncating_model(mock):
     assert res["3xtf32"][0] < 1e-4 and res["3xtf32"][1] < 2e-2, res
     assert res["tf32"][1] > 10 * res["3xtf32"][1], res
     assert res["tf32"][0] > 10 * res["3xtf32"][0], res  # the model really does lose the low operand bits in the default mode
+
+
+def test_backward_order_with_a_forward_branch():
+    """Engine._backward_order on a synthetic tape shaped like PMF's: camera closures [0, 14) = stem+layer1..layer4 (marks at
+    3, 6, 9, 12) + decoder [12, 14), LiDAR closures [14, 30) with the four feature-map copies at 16, 20, 24, 28.  Every tape
+    index runs exactly once, in an order that respects the hand-over rules documented in the method."""
+    from pmf_b200 import engine as eng
+
+    class Root:
+        ready = object()
+
+    roots = [Root() for _ in range(4)]
+    tape = [lambda: None for _ in range(30)]
+    W = [16, 20, 24, 28]
+    for r, wi in zip(roots, W):
+        def cp():
+            return None
+        cp.copy_src_root = r
+        tape[wi] = cp
+
+    class Stub:
+        pass
+    E = Stub()
+    E.tape, E.use_branch = tape, True
+    E._branch_span = [0, 14]
+    E._marks = list(zip(roots, [3, 6, 9, 12]))
+    E._waits = list(zip(roots, W))
+    old = eng.BWD_BRANCH
+    try:
+        eng.BWD_BRANCH = True
+        order = eng.Engine._backward_order(E)
+        eng.BWD_BRANCH = False
+        plain = eng.Engine._backward_order(E)
+    finally:
+        eng.BWD_BRANCH = old
+    assert [e[1] for e in plain] == list(range(29, -1, -1)) and all(e[2] == "main" for e in plain)
+    fns = [e for e in order if e[0] == "fn"]
+    assert sorted(e[1] for e in fns) == list(range(30))
+    pos = {e[1]: i for i, e in enumerate(order) if e[0] == "fn"}
+    tag = {e[1]: e[2] for e in fns}
+    assert all(tag[i] == "cam" for i in range(14)) and all(tag[i] == "main" for i in range(14, 30))
+    # each chain keeps its own reversed order
+    for chain in (range(14), range(14, 30)):
+        idx = sorted(chain, key=lambda i: pos[i])
+        assert idx == sorted(idx, reverse=True)
+    assert pos[13] < pos[12] < min(pos[i] for i in range(12))          # decoder first on the camera chain
+    wait_d = order.index(("wait", "main", "D"))
+    assert order.index(("rec", "cam", "D")) < wait_d < pos[28]         # the LiDAR chain waits for it before its first copy
+    for j, w in ((4, 24), (3, 20), (2, 16)):                             # layer j released after W[j-2]
+        lo, hi = [3, 6, 9, 12][j - 2], [3, 6, 9, 12][j - 1]
+        first = min(pos[i] for i in range(lo, hi))
+        assert pos[w] < order.index(("rec", "main", "W%d" % w)) < order.index(("wait", "cam", "W%d" % w)) < first
+    assert min(pos[i] for i in range(0, 3)) > max(pos[i] for i in range(3, 6))   # layer 1 + stem after layer 2
+    # a broken hand-over record (copy closure not where expected) falls back to the plain order
+    E._waits[1] = (roots[1], 21)
+    eng.BWD_BRANCH = True
+    try:
+        assert eng.Engine._backward_order(E) == plain
+    finally:
+        eng.BWD_BRANCH = old

@@ -400,6 +400,41 @@ def test_pmf_cuda_graph_replay_matches_eager(dev):
     assert torch.equal(e0[0], e1[0]) and torch.equal(e0[1], e1[1])
 
 
+def test_backward_branch_order_matches_plain_order(dev):
+    """The opt-in backward schedule (PMFB_BWD_BRANCH: camera-stream closures on a second auxiliary stream, Engine.
+    _backward_order) must give the gradients of the plain reversed-tape order — eagerly and replayed; only the order in
+    which the shared feature maps' gradients accumulate differs (fp32 rounding)."""
+    from pmf_b200 import engine as eng
+    feat, _, label = synth.frame_tensor(2, 64, 96, seed=19)
+    tgt = label.unsqueeze(1).to(dev)
+    res = {}
+    old = eng.BWD_BRANCH
+    try:
+        for flag in (False, True):
+            eng.BWD_BRANCH = flag
+            m, sd = _model(dev)
+            m.train()
+            for mod in m.modules():
+                if isinstance(mod, torch.nn.Dropout2d):
+                    mod.eval()
+            x = feat.to(dev)
+            grads = []
+            for it in range(3):  # eager, capture + replay, replay
+                m.load_state_dict(sd)
+                for p in m.parameters():
+                    p.grad = None
+                lid, cam = m(x[:, 0:5], x[:, 5:8])
+                (-(torch.log(lid.gather(1, tgt).clamp_min(1e-8)).mean() + torch.log(cam.gather(1, tgt).clamp_min(1e-8)).mean())).backward()
+                grads.append({n: p.grad.clone() for n, p in m.named_parameters()})
+            res[flag] = grads
+    finally:
+        eng.BWD_BRANCH = old
+    for it in range(3):
+        worst = max(_l2(res[True][it][n], res[False][it][n], 1e-3 * float(res[False][it][n.rsplit(".", 1)[0] + ".weight"].double().norm()))
+                    for n in res[False][it])
+        assert worst < 1e-3, (it, worst)
+
+
 def test_pmf_frame_parallel_and_full_size(dev):
     """Size-independent properties at the BASELINE shape (480x640): probabilities are normalised and finite, and the
     eval forward is frame-parallel (a frame's output does not depend on its batch mates) — the property the DDP
