@@ -222,6 +222,7 @@ def epmf_salsanext_fusion(E, pcd, feats, p, nclasses):
     img = feats[0]
     cat = E.new(n, h // 2, w // 2, b + img.c, needs_grad=False)
     sparse_context_block(E, d, p + ".downCntx3", out=cat.slice(0, b))
+    E.wait_ready(img)
     E.copy(img, cat.slice(b, b + img.c))
     x = fusion_block(E, cat, b, p + ".fusionblock_1")
     skips = []
@@ -232,6 +233,7 @@ def epmf_salsanext_fusion(E, pcd, feats, p, nclasses):
             img = feats[i + 1]
             cat = E.new(n, x.shape[1] // 2, x.shape[2] // 2, c + img.c, needs_grad=False)
             _, skip = res_block(E, x, rb, pooling=True, drop_out=(i > 0), pool_out=cat.slice(0, c))
+            E.wait_ready(img)
             E.copy(img, cat.slice(c, c + img.c))
             x = fusion_block(E, cat, c, "%s.fusionblock_%d" % (p, i + 2))
         else:
@@ -273,8 +275,10 @@ def epmf_rgb_decoder(E, feats, lidar_feature, p):
 
 def epmf_forward_packed(E, pcd, img7, backbone, nclasses):
     """EPMFNet.forward, epmf_net.py:209-216, from the packed NHWC inputs."""
-    feats = resnet_encoder(E, img7, "camera_stream_encoder", backbone)
+    with E.branch():  # the camera encoder runs next to the LiDAR stream (the decoder needs the LiDAR stream's ASPP output)
+        feats = resnet_encoder(E, img7, "camera_stream_encoder", backbone)
     lidar_logits, lidar_feature = epmf_salsanext_fusion(E, pcd, feats, "lidar_stream", nclasses)
+    E.join_branch()
     camera_logits = epmf_rgb_decoder(E, feats, lidar_feature, "camera_stream_decoder")
     lidar = E.softmax_nchw(lidar_logits, nclasses)
     camera = E.softmax_nchw(camera_logits, nclasses)
