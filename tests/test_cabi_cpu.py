@@ -57,9 +57,11 @@ def test_struct_layout_matches_c():
     #include <stdio.h>
     #include "pmfb.h"
     #include <stddef.h>
-    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pmfb_view), sizeof(pmfb_epilogue), sizeof(pmfb_tma_src),
+    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pmfb_view), sizeof(pmfb_epilogue), sizeof(pmfb_tma_src),
                        sizeof(pmfb_conv_desc), sizeof(pmfb_wgrad_desc), sizeof(pmfb_weight_job),
-                       offsetof(pmfb_weight_job, c_out), offsetof(pmfb_weight_job, start), offsetof(pmfb_conv_desc, bn_stats));
+                       offsetof(pmfb_weight_job, c_out), offsetof(pmfb_weight_job, start), offsetof(pmfb_conv_desc, bn_stats),
+                       offsetof(pmfb_conv_desc, out_half), sizeof(pmfb_bn_fuse), offsetof(pmfb_bn_fuse, momentum),
+                       offsetof(pmfb_bn_fuse, alpha_out));
                 return 0; }
     '''
     import tempfile
@@ -69,7 +71,8 @@ def test_struct_layout_matches_c():
         sizes = [int(x) for x in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(_lib.View), C.sizeof(_lib.Epilogue), C.sizeof(_lib.TmaSrc), C.sizeof(_lib.ConvDesc),
                      C.sizeof(_lib.WgradDesc), C.sizeof(_lib.WeightJob), _lib.WeightJob.c_out.offset, _lib.WeightJob.start.offset,
-                     _lib.ConvDesc.bn_stats.offset]
+                     _lib.ConvDesc.bn_stats.offset, _lib.ConvDesc.out_half.offset, C.sizeof(_lib.BnFuse), _lib.BnFuse.momentum.offset,
+                     _lib.BnFuse.alpha_out.offset]
 
 
 def test_bench_reference_arm_json_contract():
