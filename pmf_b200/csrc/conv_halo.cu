@@ -10,7 +10,8 @@
 // per tap.  The kernel is persistent (one CTA per SM walks the tile list), keeps up to two accumulator sets in TMEM so
 // the epilogue of tile i overlaps the MMAs of tile i+1, and processes MT stacked 128-pixel tiles per weight fetch.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5 epilogue.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..9 epilogue (two per TMEM
+// lane quadrant).
 #include <stdlib.h>
 
 #include <cuda_fp16.h>
