@@ -9,6 +9,11 @@ and tests/golden/pmf_*.npz (see oracle/__init__.py).
 ``nn.BatchNorm2d.train()`` does; running-stat side effects are returned in ``new_stats`` instead of being
 applied in place.  Dropout2d sites take explicit masks (``dropout`` dict: site -> (B,C,1,1) tensor holding
 0 or 1/(1-p)); a missing site means "no dropout" (eval semantics).
+
+Two optional EMULATION switches of ``Ctx`` (off by default; what is pinned to the reference is the plain fp32 path):
+``tf32=True`` rounds conv operands to tf32, ``half_pre_bn=True`` rounds the input of a training-mode BatchNorm to fp16 where
+the device's "f16" mode stores it in fp16.  They exist so that the kernel tests can tell wiring errors (O(1)) from the
+expected rounding noise: the device result is compared with an oracle that rounds at the same points.
 """
 import math
 
