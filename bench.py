@@ -816,7 +816,10 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
     prev = os.environ.get("PMFB_CUDA_GRAPH")
     prev_side = os.environ.get("PMFB_WGRAD_STREAM")
     os.environ["PMFB_CUDA_GRAPH"] = "0"
-    os.environ["PMFB_WGRAD_STREAM"] = "0"  # per-launch event timing needs every kernel on the launching stream
+    os.environ["PMFB_WGRAD_STREAM"] = "0"  # per-launch event timing needs every kernel on the launching stream ...
+    from pmf_b200 import engine as _eng
+    prev_branch = _eng.FWD_BRANCH
+    _eng.FWD_BRANCH = False                # ... and alone on the GPU: no camera-stream branch next to the LiDAR stream
     try:
         step_fn()  # eager warm-up (allocator)
         torch.cuda.synchronize()
@@ -828,6 +831,7 @@ def kernel_roofline(step_fn, dev, ms_per_step, peak_tf, peak_src):
         torch.cuda.synchronize()
     finally:
         L.call = orig
+        _eng.FWD_BRANCH = prev_branch
         if prev is None:
             os.environ.pop("PMFB_CUDA_GRAPH", None)
         else:
