@@ -412,7 +412,9 @@ def _side_stream(device, which=0):
 
 
 class _Scratch:
-    """Bump allocator over one zero-initialised buffer (fp64 reduction cells) or an uninitialised fp32 one."""
+    """Bump allocator over one zero-initialised buffer (fp64 reduction cells) or an uninitialised fp32 one.  ``stream`` is a
+    handle or a callable returning the engine's CURRENT stream handle: a chunk that has to be added in the middle of a pass
+    is zeroed on the stream whose kernels are about to use it (the pass may be on an auxiliary stream, Engine.branch)."""
 
     def __init__(self, dtype, n, device, stream, zero):
         self.dtype, self.n, self.device, self.stream, self.zero = dtype, n, device, stream, zero
@@ -422,7 +424,8 @@ class _Scratch:
     def _new_chunk(self):
         self.buf = torch.empty(self.n, device=self.device, dtype=self.dtype)
         if self.zero:
-            L.call("pmfb_memset_zero", self.buf.data_ptr(), self.n * self.buf.element_size(), self.stream)
+            st = self.stream() if callable(self.stream) else self.stream
+            L.call("pmfb_memset_zero", self.buf.data_ptr(), self.n * self.buf.element_size(), st)
         self.chunks.append(self.buf)
         self.pos = 0
 
@@ -470,8 +473,8 @@ class Engine:
         self.segments = None
         self.tape = []
         self.dropout = dropout  # see mask_for
-        self.d64 = _Scratch(torch.float64, 1 << 17, device, self.st, zero=True)
-        self.f32 = _Scratch(torch.float32, 1 << 17, device, self.st, zero=False)
+        self.d64 = _Scratch(torch.float64, 1 << 18, device, lambda: self.st, zero=True)
+        self.f32 = _Scratch(torch.float32, 1 << 17, device, lambda: self.st, zero=False)
         self._dpre16 = None
         self.param_grads = {}
         self.flat_views = None  # graph mode: {param name: view into one flat gradient buffer}
@@ -1475,8 +1478,7 @@ class Engine:
 
     def begin_backward(self):
         self.st = torch.cuda.current_stream(self.device).cuda_stream
-        self.d64 = _Scratch(torch.float64, 1 << 18, self.device, self.st, zero=True)  # one chunk for the whole backward: a
-        self.f32.stream = self.st                                                     # new one would be zeroed on THIS stream only
+        self.d64 = _Scratch(torch.float64, 1 << 18, self.device, lambda: self.st, zero=True)
         if self._wg_arena is not None:
             L.call("pmfb_memset_zero", self._wg_arena.data_ptr(), self._wg_arena.numel() * 4, self.st)
 
@@ -1486,9 +1488,6 @@ class Engine:
         self.st = torch.cuda.current_stream(self.device).cuda_stream
         if k == 0:
             self.begin_backward()
-        else:
-            self.d64.stream = self.st
-            self.f32.stream = self.st
         self._run_entries(self.segments[k][0])
         self.join_side()
         tab = self._unpack_tables[k] if self._unpack_tables else None
